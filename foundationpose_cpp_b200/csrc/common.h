@@ -1,0 +1,54 @@
+// Shared host-side helpers: error reporting for the C ABI, CUDA call checking.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+
+namespace fpb {
+
+// Last error message of the calling thread (returned by fpb200_last_error()).
+inline std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+inline int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define FPB_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      char _b[512];                                                                         \
+      snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                \
+               cudaGetErrorString(_e));                                                     \
+      throw ::fpb::CudaError(_b);                                                           \
+    }                                                                                       \
+  } while (0)
+
+#define FPB_REQUIRE(cond, ...)                                                              \
+  do {                                                                                      \
+    if (!(cond)) {                                                                          \
+      char _b[512];                                                                         \
+      snprintf(_b, sizeof(_b), __VA_ARGS__);                                                \
+      throw std::invalid_argument(std::string(_b));                                         \
+    }                                                                                       \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
+
+}  // namespace fpb

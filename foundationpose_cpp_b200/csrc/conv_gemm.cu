@@ -1,0 +1,418 @@
+// tcgen05 implicit-GEMM convolution kernel (see conv_gemm.h).
+//
+// Roles inside one persistent CTA (192 threads, one CTA per SM):
+//   warp 0, lane 0 : TMA producer.  Per k-block (one filter tap x 64 input channels) it loads a
+//                    128-row activation box and a block_n-row weight box into a smem ring.
+//   warp 1, lane 0 : MMA issuer.  Four 128 x block_n x 16 tcgen05.mma per k-block, accumulating in
+//                    one of two TMEM accumulator stages.
+//   warps 2..5     : epilogue.  Each thread owns one output pixel (TMEM lane); reads 32 columns
+//                    at a time with tcgen05.ld and applies bias / residual / ReLU / pos-table.
+// The two TMEM stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "conv_gemm.h"
+
+#include <cstdio>
+#include <cstring>
+
+#include "ptx.cuh"
+
+namespace fpb {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KB
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = BN * kGemmBlockK * 2;
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr size_t kSmem =
+      1024 /*alignment slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + C::kStages * kABytes;
+  const uint32_t bar_base = b_base + C::kStages * C::kBBytes;
+  // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);
+      ptx::mbar_init(tempty_bar(s), 128);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&p.tm_a);
+    ptx::prefetch_tensormap(&p.tm_b);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_img;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int kblocks = p.num_taps * p.cblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = tile / p.n_tiles;
+        const int x0 = (mt % p.tiles_x) * p.bw;
+        const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
+        const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
+        int kb = 0;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const int cx = x0 + p.tap_dx[t];
+          const int cy = y0 + p.tap_dy[t];
+          const int cp = p.tap_plane[t];
+          for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            ptx::mbar_expect_tx(full_bar(stage), kABytes + C::kBBytes);
+            ptx::tma_load_5d(a_base + stage * kABytes, &p.tm_a, full_bar(stage), cb * kGemmBlockK,
+                             cx, cy, cp, n0);
+            ptx::tma_load_2d(b_base + stage * C::kBBytes, &p.tm_b, full_bar(stage),
+                             kb * kGemmBlockK, nt * BN);
+            if (++stage == C::kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kGemmBlockM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_base + stage * kABytes);
+          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(b_base + stage * C::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kGemmBlockK / 16; ++k) {
+            // advancing 16 fp16 along K inside the 128-byte swizzle row = +32 B = +2 in the
+            // descriptor's 16-byte address units
+            ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(empty_bar(stage));
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int rx = row % p.bw;
+    const int ry = (row / p.bw) % p.bh;
+    const int rn = row / (p.bw * p.bh);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int x = (mt % p.tiles_x) * p.bw + rx;
+      const int y = ((mt / p.tiles_x) % p.tiles_y) * p.bh + ry;
+      const int n = (mt / (p.tiles_x * p.tiles_y)) * p.bn + rn;
+      const bool valid = (x < p.W) && (y < p.H) && (n < p.n_img);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+
+      const int nn = n % p.img_mod;
+      const int coff = (n / p.img_mod) * p.half_coff + nt * BN;
+      long long opix;
+      if (p.out_phase_split) {
+        const int plane = (y & 1) * 2 + (x & 1);
+        opix = ((static_cast<long long>(nn) * 4 + plane) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) +
+               (x >> 1);
+      } else {
+        opix = (static_cast<long long>(nn) * p.H + y) * p.W + x;
+      }
+      __half* optr = p.out + opix * p.out_ld + coff;
+      const __half* rptr =
+          p.residual
+              ? p.residual + ((static_cast<long long>(n) * p.H + y) * p.W + x) * p.res_ld + nt * BN
+              : nullptr;
+      const float* pptr =
+          p.post_add ? p.post_add + (static_cast<long long>(y) * p.W + x) * p.cout + nt * BN
+                     : nullptr;
+      const float* bptr = p.bias + nt * BN;
+
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bptr + c0 + j));
+            v[j + 0] = __uint_as_float(r[j + 0]) + b.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+          }
+          if (rptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rptr + c0 + j));
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (pptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(pptr + c0 + j));
+              v[j + 0] += a.x;
+              v[j + 1] += a.y;
+              v[j + 2] += a.z;
+              v[j + 3] += a.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(optr + c0 + j) = u;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+
+}  // namespace
+
+const char* conv_gemm_init() {
+  if (g_encode) return nullptr;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return "cuTensorMapEncodeTiled not available from the CUDA driver";
+  e = cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)Cfg<64>::kSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)Cfg<128>::kSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)Cfg<256>::kSmem);
+  if (e != cudaSuccess) return "cudaFuncSetAttribute(max dynamic smem) failed (not an sm_100a device?)";
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return nullptr;
+}
+
+void taps_3x3_s1(ConvGemmDesc* d) {
+  d->num_taps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      d->tap_dy[ky * 3 + kx] = (int8_t)(ky - 1);
+      d->tap_dx[ky * 3 + kx] = (int8_t)(kx - 1);
+      d->tap_plane[ky * 3 + kx] = 0;
+    }
+}
+
+void taps_3x3_s2_phase(ConvGemmDesc* d) {
+  // input pixel (2*oy + ky - 1, 2*ox + kx - 1): parity = (k-1)&1, half-res offset = -1 for k==0
+  d->num_taps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int py = (ky == 1) ? 0 : 1, px = (kx == 1) ? 0 : 1;
+      d->tap_dy[ky * 3 + kx] = (int8_t)(ky == 0 ? -1 : 0);
+      d->tap_dx[ky * 3 + kx] = (int8_t)(kx == 0 ? -1 : 0);
+      d->tap_plane[ky * 3 + kx] = (int8_t)(py * 2 + px);
+    }
+}
+
+void taps_stem7_rows(ConvGemmDesc* d) {
+  // input row 2*oy + ky - 3: parity r = (ky-3) mod 2, half-row offset q = floor((ky-3)/2)
+  d->num_taps = 7;
+  for (int ky = 0; ky < 7; ++ky) {
+    const int o = ky - 3;
+    const int r = ((o % 2) + 2) % 2;
+    const int q = (o - r) / 2;
+    d->tap_dy[ky] = (int8_t)q;
+    d->tap_dx[ky] = 0;
+    d->tap_plane[ky] = (int8_t)r;
+  }
+}
+
+const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
+  if (const char* e = conv_gemm_init()) return e;
+  if (d.bw * d.bh * d.bn != kGemmBlockM) return "conv_gemm: bw*bh*bn must be 128";
+  if (d.cin % kGemmBlockK != 0) return "conv_gemm: cin must be a multiple of 64";
+  if (d.num_taps < 1 || d.num_taps > kMaxTaps) return "conv_gemm: bad tap count";
+  int bn_tile = 0;
+  if (d.cout % 256 == 0) bn_tile = 256;
+  else if (d.cout % 128 == 0) bn_tile = 128;
+  else if (d.cout % 64 == 0) bn_tile = 64;
+  else return "conv_gemm: cout must be a multiple of 64";
+  const int out_ld = d.out_ld ? d.out_ld : d.cout;
+  if (out_ld % 8 || d.half_coff % 8) return "conv_gemm: output leading dims must be multiples of 8";
+  if (d.out_phase_split && ((d.out_h | d.out_w) & 1)) return "conv_gemm: phase-split needs even H, W";
+
+  ConvGemmParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  {
+    const long long sw = d.stride_w ? d.stride_w : 2LL * d.cin;
+    const long long sh = d.stride_h ? d.stride_h : sw * d.in_w;
+    const long long sp = d.stride_plane ? d.stride_plane : sh * d.in_h;
+    const long long si = d.stride_img ? d.stride_img : sp * d.planes;
+    cuuint64_t dims[5] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.in_h,
+                          (cuuint64_t)d.planes, (cuuint64_t)d.n_img};
+    cuuint64_t strides[4] = {(cuuint64_t)sw, (cuuint64_t)sh, (cuuint64_t)sp, (cuuint64_t)si};
+    cuuint32_t box[5] = {kGemmBlockK, (cuuint32_t)d.bw, (cuuint32_t)d.bh, 1, (cuuint32_t)d.bn};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)d.in, dims, strides,
+                          box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      static char msg[128];
+      snprintf(msg, sizeof(msg), "conv_gemm: cuTensorMapEncodeTiled(A) failed with CUresult %d", (int)r);
+      return msg;
+    }
+  }
+  {
+    const long long ktot = (long long)d.num_taps * d.cin;
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)(ktot * 2)};
+    cuuint32_t box[2] = {kGemmBlockK, (cuuint32_t)bn_tile};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)d.weight, dims,
+                          strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      static char msg[128];
+      snprintf(msg, sizeof(msg), "conv_gemm: cuTensorMapEncodeTiled(B) failed with CUresult %d", (int)r);
+      return msg;
+    }
+  }
+  p.bw = d.bw;
+  p.bh = d.bh;
+  p.bn = d.bn;
+  p.W = d.out_w;
+  p.H = d.out_h;
+  p.n_img = d.n_img;
+  p.tiles_x = (d.out_w + d.bw - 1) / d.bw;
+  p.tiles_y = (d.out_h + d.bh - 1) / d.bh;
+  p.tiles_img = (d.n_img + d.bn - 1) / d.bn;
+  p.n_tiles = d.cout / bn_tile;
+  p.num_taps = d.num_taps;
+  p.cblocks = d.cin / kGemmBlockK;
+  memcpy(p.tap_dx, d.tap_dx, sizeof(p.tap_dx));
+  memcpy(p.tap_dy, d.tap_dy, sizeof(p.tap_dy));
+  memcpy(p.tap_plane, d.tap_plane, sizeof(p.tap_plane));
+  p.bias = d.bias;
+  p.residual = d.residual;
+  p.res_ld = d.res_ld ? d.res_ld : d.cout;
+  p.post_add = d.post_add;
+  p.out = d.out;
+  p.relu = d.relu ? 1 : 0;
+  p.cout = d.cout;
+  p.out_phase_split = d.out_phase_split ? 1 : 0;
+  p.out_ld = out_ld;
+  p.img_mod = d.img_mod ? d.img_mod : d.n_img;
+  p.half_coff = d.half_coff;
+
+  plan->block_n = bn_tile;
+  const long long tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles;
+  const int cap = d.max_ctas > 0 ? d.max_ctas : g_num_sms;
+  plan->grid = (int)(tiles < cap ? tiles : cap);
+  plan->smem = bn_tile == 256 ? Cfg<256>::kSmem : (bn_tile == 128 ? Cfg<128>::kSmem : Cfg<64>::kSmem);
+  plan->flops = 2.0 * d.n_img * d.out_h * d.out_w * (double)d.cout * d.num_taps * d.cin;
+  return nullptr;
+}
+
+cudaError_t launch_conv_gemm(const ConvGemmPlan& plan, cudaStream_t stream) {
+  if (plan.grid <= 0) return cudaSuccess;
+  switch (plan.block_n) {
+    case 256:
+      conv_gemm_kernel<256><<<plan.grid, kThreads, plan.smem, stream>>>(plan.p);
+      break;
+    case 128:
+      conv_gemm_kernel<128><<<plan.grid, kThreads, plan.smem, stream>>>(plan.p);
+      break;
+    default:
+      conv_gemm_kernel<64><<<plan.grid, kThreads, plan.smem, stream>>>(plan.p);
+      break;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace fpb

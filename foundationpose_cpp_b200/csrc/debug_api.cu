@@ -1,0 +1,70 @@
+// Stage-level C-ABI entry points used by the parity tests and micro-benchmarks: they run one
+// kernel of the hot path on caller-provided DEVICE pointers.  Declared in include/fpb200.h.
+#include <cuda_runtime.h>
+
+#include "../../include/fpb200.h"
+#include "common.h"
+#include "conv_gemm.h"
+
+using namespace fpb;
+
+extern "C" int fpb200_debug_conv_gemm(const fpb200_conv_desc* c, int repeat, float* ms_out) {
+  try {
+    ConvGemmDesc d;
+    d.in = static_cast<const __half*>(c->in);
+    d.n_img = c->n_img;
+    d.planes = c->planes;
+    d.in_h = c->in_h;
+    d.in_w = c->in_w;
+    d.cin = c->cin;
+    d.stride_w = c->stride_w;
+    d.stride_h = c->stride_h;
+    d.stride_plane = c->stride_plane;
+    d.stride_img = c->stride_img;
+    d.out_h = c->out_h;
+    d.out_w = c->out_w;
+    d.bw = c->bw;
+    d.bh = c->bh;
+    d.bn = c->bn;
+    switch (c->tap_kind) {
+      case FPB200_TAPS_1X1: d.num_taps = 1; break;
+      case FPB200_TAPS_3X3_S1: taps_3x3_s1(&d); break;
+      case FPB200_TAPS_3X3_S2_PHASE: taps_3x3_s2_phase(&d); break;
+      case FPB200_TAPS_STEM7_ROWS: taps_stem7_rows(&d); break;
+      default: return fail(FPB200_ERR_INVALID, "unknown tap_kind %d", c->tap_kind);
+    }
+    d.weight = static_cast<const __half*>(c->weight);
+    d.cout = c->cout;
+    d.bias = c->bias;
+    d.residual = static_cast<const __half*>(c->residual);
+    d.res_ld = c->res_ld;
+    d.post_add = c->post_add;
+    d.out = static_cast<__half*>(c->out);
+    d.relu = c->relu != 0;
+    d.out_phase_split = c->out_phase_split != 0;
+    d.out_ld = c->out_ld;
+    d.img_mod = c->img_mod;
+    d.half_coff = c->half_coff;
+    d.max_ctas = c->max_ctas;
+    ConvGemmPlan plan;
+    if (const char* e = build_conv_gemm(d, &plan)) return fail(FPB200_ERR_INVALID, "%s", e);
+    cudaEvent_t e0, e1;
+    FPB_CUDA(cudaEventCreate(&e0));
+    FPB_CUDA(cudaEventCreate(&e1));
+    FPB_CUDA(launch_conv_gemm(plan, 0));  // warm-up + the result the caller checks
+    FPB_CUDA(cudaEventRecord(e0, 0));
+    for (int i = 0; i < repeat; ++i) FPB_CUDA(launch_conv_gemm(plan, 0));
+    FPB_CUDA(cudaEventRecord(e1, 0));
+    FPB_CUDA(cudaDeviceSynchronize());
+    float ms = 0.f;
+    FPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = repeat > 0 ? ms / repeat : 0.f;
+    return FPB200_OK;
+  } catch (const std::exception& e) {
+    return fail(FPB200_ERR_CUDA, "%s", e.what());
+  }
+}
+
+extern "C" const char* fpb200_last_error(void) { return last_error().c_str(); }

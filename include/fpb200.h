@@ -1,0 +1,151 @@
+/* fpb200 — C ABI of the B200-native FoundationPose Register/Track hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point
+ * names the reference interface it replaces (paths under zz990099/foundationpose_cpp):
+ *   fp/  = detection_6d_foundationpose/     edt/ = easy_deploy_tool/
+ *
+ * Conventions
+ *   - 4x4 poses are 16 floats, COLUMN-major (Eigen::Matrix4f storage, as the reference copies them
+ *     to the device: fp/src/foundationpose_render.cpp:836); a pose maps the CENTRED mesh into the
+ *     OpenCV camera frame (fp/src/foundationpose.cpp:225,262).
+ *   - rgb is u8 [h,w,3] RGB, depth is f32 [h,w] metres, mask is u8 [h,w] (>0 = object), all HOST
+ *     pointers borrowed for the call (fp/include/detection_6d_foundationpose/foundationpose.hpp:16-77).
+ *   - every function returns FPB200_OK (0) or a negative error code; fpb200_last_error() returns
+ *     the calling thread's last message.  (The reference returns bool + glog; 0 <-> true.)
+ *   - a session is NOT thread-safe per target mesh, like the reference's renderer scratch
+ *     (fp/src/foundationpose_render.hpp:129-152).
+ */
+#ifndef FPB200_H_
+#define FPB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  FPB200_OK = 0,
+  FPB200_ERR_INVALID = -1, /* bad argument (reference: CHECK_STATE false / std::invalid_argument) */
+  FPB200_ERR_CUDA = -2,    /* CUDA failure (reference: CHECK_CUDA -> false) */
+  FPB200_ERR_IO = -3,      /* weight file missing/corrupt (reference: engine load failure) */
+  FPB200_ERR_STATE = -4,   /* call order violated, e.g. stage call before upload */
+  FPB200_ERR_NO_DEPTH = -5 /* empty mask / no valid depth (fp/src/foundationpose_sampling.cpp:250-298) */
+};
+
+typedef struct fpb200_session fpb200_session;
+
+/* What a BaseMeshLoader yields (fp/include/detection_6d_foundationpose/mesh_loader.hpp:15-62).
+ * vertices are the loader's raw vertices; the library subtracts `center` like
+ * fp/src/foundationpose_render.cpp:396-398 and flips texcoords to (u,1-v) like :405-406. */
+typedef struct {
+  const char* name;
+  const float* vertices;  /* [num_vertices,3] */
+  const float* normals;   /* [num_vertices,3] */
+  const float* texcoords; /* [num_vertices,2] */
+  const int32_t* faces;   /* [num_faces,3] */
+  const uint8_t* texture; /* [tex_h,tex_w,3] RGB */
+  int num_vertices, num_faces, tex_h, tex_w;
+  float diameter;
+  float center[3];
+} fpb200_mesh;
+
+typedef struct {
+  int device;        /* CUDA device ordinal */
+  int max_hyps;      /* capacity in hypotheses (reference: 252, fp/src/foundationpose.cpp:86) */
+  int shard_rank;    /* multi-GPU: this process handles hypotheses of rank shard_rank ... */
+  int shard_world;   /* ... out of shard_world equal contiguous shards (1 = everything) */
+  int use_cuda_graph; /* capture the per-iteration launch sequence into CUDA graphs */
+} fpb200_options;
+
+void fpb200_default_options(fpb200_options* o);
+
+/* Replaces CreateFoundationPoseModel (fp/include/.../foundationpose.hpp:99-105) together with the
+ * two CreateTrtInferCore calls that feed it (edt/inference_core/trt_core/include/trt_core/trt_core.h:26-30):
+ * the weight files take the place of the serialized TensorRT engines. */
+int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], int max_h, int max_w,
+                  const char* refiner_weights, const char* scorer_weights,
+                  const fpb200_options* opts, fpb200_session** out);
+void fpb200_destroy(fpb200_session* s);
+
+/* Base6DofDetectionModel::Register (fp/src/foundationpose.cpp:181-228). */
+int fpb200_register(fpb200_session* s, const uint8_t* rgb, const float* depth, const uint8_t* mask,
+                    int h, int w, const char* target_name, int refine_itr, float out_pose[16]);
+/* Base6DofDetectionModel::Track (fp/src/foundationpose.cpp:230-265). */
+int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w,
+                 const float hyp_pose[16], const char* target_name, int refine_itr,
+                 float out_pose[16]);
+
+/* ---- stage-level entry points (the reference's private seams), used by tests / multi-GPU ---- */
+
+/* UploadDataToDevice + depth->xyz (fp/src/foundationpose.cpp:267-315, fp/src/foundationpose_utils.cu:3-75). */
+int fpb200_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w);
+/* FoundationPoseSampler::GetHypPoses (fp/src/foundationpose_sampling.cpp:344-394): fills the
+ * session's hypothesis set with the 252-pose grid at the guessed translation. */
+int fpb200_sample_hypotheses(fpb200_session* s, const uint8_t* mask, const char* target_name);
+/* Replace the session's hypothesis set (n col-major 4x4).  Track does this with n = 1. */
+int fpb200_set_hypotheses(fpb200_session* s, const float* poses, int n, const char* target_name);
+int fpb200_get_hypotheses(fpb200_session* s, float* poses, int capacity, int* n);
+/* FoundationPoseRenderer::RenderAndTransform (fp/src/foundationpose_render.hpp:29-37) on the
+ * session's current hypotheses: fills the packed network input (render + observed crops). */
+int fpb200_render_and_transform(fpb200_session* s, float crop_ratio);
+/* One refine iteration = RefinePreProcess + refiner SyncInfer + RefinePostProcess
+ * (fp/src/foundationpose.cpp:317-406); hypotheses are updated in place on the device. */
+int fpb200_refine_step(fpb200_session* s);
+/* ScorePreprocess + scorer SyncInfer up to the per-hypothesis 512-d feature
+ * (fp/src/foundationpose.cpp:408-430).  With shard_world > 1 only the local shard is computed. */
+int fpb200_score_features(fpb200_session* s);
+/* Device pointer + row count of the local shard's features [n_local,512] f32 and of the full
+ * buffer [n,512] the tail reads; a multi-GPU host all-gathers into the latter. */
+int fpb200_feature_buffers(fpb200_session* s, void** local_dev, int* n_local, int* local_offset,
+                           void** all_dev, int* n_all);
+/* Cross-hypothesis attention + Linear + argmax (scorer tail) and ScorePostProcess
+ * (fp/src/foundationpose.cpp:432-446, fp/src/foundationpose_decoder.cu:24-35). */
+int fpb200_score_finish(fpb200_session* s, int* best_index, float out_pose[16]);
+
+/* Copy a named device buffer of the session to the host (tests): "render_input" / "transf_input"
+ * (f16 [n,160,160,8] packed rgb+xyz+2 pad), "xyz_map" (f32 [h,w,3]), "scores" (f32 [n]),
+ * "trans" / "rot" (f32 [n,3]), "features" (f32 [n,512]), "rast_id" (i32 [n,160,160]),
+ * "crop_tf" (f32 [n,9] row-major), "bbox2d" (f32 [n,4]), "depth_filtered" (f32 [h,w]). */
+int fpb200_read_buffer(fpb200_session* s, const char* name, void* host_dst, size_t capacity_bytes,
+                       size_t* bytes_written);
+/* Device-side duration of the stages of the last Register/Track (CUDA events), in ms:
+ * [0] upload+xyz [1] sampler [2] refine preprocess [3] refiner net [4] score preprocess
+ * [5] scorer net [6] tail; returns the number filled. */
+int fpb200_last_timings(fpb200_session* s, float* ms, int capacity);
+/* Algorithmic FLOPs of one refiner / scorer forward per hypothesis, from the loaded layer list. */
+int fpb200_flops_per_hypothesis(fpb200_session* s, double* refiner, double* scorer);
+/* Number of kernel launches issued by the last Register/Track call. */
+int fpb200_last_launch_count(fpb200_session* s);
+
+/* ---- kernel-level debug entry points (DEVICE pointers) ---- */
+enum {
+  FPB200_TAPS_1X1 = 0,
+  FPB200_TAPS_3X3_S1 = 1,
+  FPB200_TAPS_3X3_S2_PHASE = 2,
+  FPB200_TAPS_STEM7_ROWS = 3
+};
+typedef struct {
+  const void* in; /* f16 */
+  int n_img, planes, in_h, in_w, cin;
+  long long stride_w, stride_h, stride_plane, stride_img; /* bytes; 0 = dense */
+  int out_h, out_w, bw, bh, bn, tap_kind;
+  const void* weight; /* f16 [cout][taps*cin] */
+  int cout;
+  const float* bias;
+  const void* residual; /* f16 or NULL */
+  int res_ld;
+  const float* post_add;
+  void* out; /* f16 */
+  int relu, out_phase_split, out_ld, img_mod, half_coff, max_ctas;
+} fpb200_conv_desc;
+/* Runs the tcgen05 implicit-GEMM kernel once (+ `repeat` timed launches; avg ms -> *ms_out). */
+int fpb200_debug_conv_gemm(const fpb200_conv_desc* desc, int repeat, float* ms_out);
+
+const char* fpb200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPB200_H_ */
