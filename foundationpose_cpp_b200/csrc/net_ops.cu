@@ -1,0 +1,302 @@
+// Non-GEMM network operators (see net_ops.h).  All HBM-bound or tiny; fp32 math, fp16 storage.
+#include "net_ops.h"
+
+#include <cfloat>
+
+namespace fpb {
+
+namespace {
+
+constexpr int kDim = 512;
+constexpr int kTok = 400;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per row of 512 channels: lane l owns channels [8l, 8l+8) and [256 + 8l, 256 + 8l + 8),
+// i.e. two coalesced 16-byte loads per operand.
+__global__ void add_layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ y,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     __half* __restrict__ out, long long rows) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[16];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = h * 256 + lane * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(x + row * kDim + c);
+    const uint4 b = *reinterpret_cast<const uint4*>(y + row * kDim + c);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __half22float2(ah[e]), fb = __half22float2(bh[e]);
+      v[h * 8 + 2 * e] = fa.x + fb.x;
+      v[h * 8 + 2 * e + 1] = fa.y + fb.y;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / kDim);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / kDim) + 1e-5f);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = h * 256 + lane * 8;
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 g = *reinterpret_cast<const float2*>(gamma + c + 2 * e);
+      const float2 b = *reinterpret_cast<const float2*>(beta + c + 2 * e);
+      oh[e] = __floats2half2_rn((v[h * 8 + 2 * e] - mean) * rstd * g.x + b.x,
+                                (v[h * 8 + 2 * e + 1] - mean) * rstd * g.y + b.y);
+    }
+    *reinterpret_cast<uint4*>(out + row * kDim + c) = o;
+  }
+}
+
+// One 1024-thread CTA per hypothesis: four groups of 256 threads each sum 100 tokens (one coalesced
+// 1 KB row per step), then the groups are combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(1024)
+token_mean_kernel(const __half* __restrict__ x, float* __restrict__ out) {
+  __shared__ float2 part[4][256];
+  const int n = blockIdx.x, grp = threadIdx.x >> 8, t256 = threadIdx.x & 255;
+  const __half2* p = reinterpret_cast<const __half2*>(x + (static_cast<long long>(n) * kTok + grp * 100) * kDim) + t256;
+  float sx = 0.f, sy = 0.f;
+#pragma unroll 4
+  for (int t = 0; t < 100; ++t) {
+    const float2 f = __half22float2(p[static_cast<long long>(t) * (kDim / 2)]);
+    sx += f.x;
+    sy += f.y;
+  }
+  part[grp][t256] = make_float2(sx, sy);
+  __syncthreads();
+  if (grp == 0) {
+    const float ax = ((part[0][t256].x + part[1][t256].x) + part[2][t256].x) + part[3][t256].x;
+    const float ay = ((part[0][t256].y + part[1][t256].y) + part[2][t256].y) + part[3][t256].y;
+    *reinterpret_cast<float2*>(out + static_cast<long long>(n) * kDim + 2 * t256) =
+        make_float2(ax * (1.f / kTok), ay * (1.f / kTok));
+  }
+}
+
+// Block = 8 rows x 8 warps; each warp produces outputs o = warp, warp+8, ... of its column slab
+// for all 8 rows, reading each weight row once (coalesced across lanes).
+constexpr int kSLRows = 8;
+__global__ void small_linear_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                    const float* __restrict__ b, float* __restrict__ out, int rows, int k,
+                                    int outs) {
+  extern __shared__ float s_in[];  // [kSLRows][k]
+  const int r0 = blockIdx.x * kSLRows;
+  for (int i = threadIdx.x; i < kSLRows * k; i += blockDim.x) {
+    const int r = i / k;
+    s_in[i] = (r0 + r < rows) ? in[static_cast<long long>(r0 + r) * k + (i - r * k)] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int o_begin = blockIdx.y * 64, o_end = min(outs, o_begin + 64);
+  for (int o = o_begin + warp; o < o_end; o += nw) {
+    float acc[kSLRows];
+#pragma unroll
+    for (int r = 0; r < kSLRows; ++r) acc[r] = 0.f;
+    const float* wr = w + static_cast<long long>(o) * k;
+    for (int c = lane; c < k; c += 32) {
+      const float wv = wr[c];
+#pragma unroll
+      for (int r = 0; r < kSLRows; ++r) acc[r] += wv * s_in[r * k + c];
+    }
+#pragma unroll
+    for (int r = 0; r < kSLRows; ++r) {
+      const float v = warp_sum(acc[r]);
+      if (lane == 0 && r0 + r < rows) out[static_cast<long long>(r0 + r) * outs + o] = v + (b ? b[o] : 0.f);
+    }
+  }
+}
+
+// One warp per (query, head): 128-d dot products with every key, softmax, weighted sum of V.
+__global__ void cross_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n) {
+  extern __shared__ float s_p[];  // [warps][n]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int item = blockIdx.x * nw + warp;
+  if (item >= n * 4) return;
+  const int qi = item >> 2, head = item & 3;
+  float* p = s_p + warp * n;
+  const float4 q = *reinterpret_cast<const float4*>(qkv + static_cast<long long>(qi) * 1536 + head * 128 + lane * 4);
+  const float scale = 0.08838834764831845f;
+  float mx = -FLT_MAX;
+  for (int j = 0; j < n; ++j) {
+    const float4 kv = *reinterpret_cast<const float4*>(qkv + static_cast<long long>(j) * 1536 + 512 + head * 128 + lane * 4);
+    float d = q.x * kv.x + q.y * kv.y + q.z * kv.z + q.w * kv.w;
+    d = warp_sum(d) * scale;
+    if (lane == 0) p[j] = d;
+    mx = fmaxf(mx, d);
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    const float e = __expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < n; ++j) {
+    const float pj = p[j];
+    const float4 v = *reinterpret_cast<const float4*>(qkv + static_cast<long long>(j) * 1536 + 1024 + head * 128 + lane * 4);
+    acc.x += pj * v.x; acc.y += pj * v.y; acc.z += pj * v.z; acc.w += pj * v.w;
+  }
+  const float inv = 1.f / sum;
+  *reinterpret_cast<float4*>(out + static_cast<long long>(qi) * 512 + head * 128 + lane * 4) =
+      make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+
+__global__ void argmax_pose_kernel(const float* __restrict__ scores, const float* __restrict__ poses, int n,
+                                   int* __restrict__ best_index, float* __restrict__ best_pose) {
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  float bv = -FLT_MAX;
+  int bi = INT_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = scores[i];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    bv = threadIdx.x < nw ? s_v[threadIdx.x] : -FLT_MAX;
+    bi = threadIdx.x < nw ? s_i[threadIdx.x] : INT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (bi == INT_MAX) bi = 0;  // all scores NaN: keep index 0 like an empty max_element walk
+    if (threadIdx.x == 0) *best_index = bi;
+    if (threadIdx.x < 16) best_pose[threadIdx.x] = poses[16 * bi + threadIdx.x];
+  }
+}
+
+// One warp per hypothesis.
+__global__ void refine_update_kernel(const float* __restrict__ mean_t, const float* __restrict__ mean_r,
+                                     const float* __restrict__ wt, const float* __restrict__ bt,
+                                     const float* __restrict__ wr, const float* __restrict__ br, float half_d,
+                                     float* __restrict__ poses, float* __restrict__ trans_out,
+                                     float* __restrict__ rot_out, int n) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  float d[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = lane; c < kDim; c += 32) {
+    const float a = mean_t[static_cast<long long>(i) * kDim + c];
+    const float b = mean_r[static_cast<long long>(i) * kDim + c];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      d[o] += a * wt[o * kDim + c];
+      d[3 + o] += b * wr[o * kDim + c];
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 6; ++o) d[o] = warp_sum(d[o]);
+  if (lane != 0) return;
+  float tr[3], ro[3];
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    tr[o] = d[o] + bt[o];
+    ro[o] = d[3 + o] + br[o];
+    trans_out[3 * i + o] = tr[o];
+    rot_out[3 * i + o] = ro[o];
+  }
+  float* p = poses + 16 * i;  // column-major
+  // t += trans * d/2
+  p[12] += tr[0] * half_d;
+  p[13] += tr[1] * half_d;
+  p[14] += tr[2] * half_d;
+  // dR = Rodrigues(v)^T, v = tanh(rot) * 20 deg; zero vector -> identity
+  const float vx = tanhf(ro[0]) * 0.349065850398865f, vy = tanhf(ro[1]) * 0.349065850398865f,
+              vz = tanhf(ro[2]) * 0.349065850398865f;
+  const float ang = sqrtf(vx * vx + vy * vy + vz * vz);
+  float rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (ang > 0.f) {
+    const float ax = vx / ang, ay = vy / ang, az = vz / ang;
+    const float c = cosf(ang), s = sinf(ang), k = 1.f - c;
+    rm[0] = c + k * ax * ax;      rm[1] = k * ax * ay - s * az; rm[2] = k * ax * az + s * ay;
+    rm[3] = k * ay * ax + s * az; rm[4] = c + k * ay * ay;      rm[5] = k * ay * az - s * ax;
+    rm[6] = k * az * ax - s * ay; rm[7] = k * az * ay + s * ax; rm[8] = c + k * az * az;
+  }
+  float r_old[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r_old[3 * r + c] = p[4 * c + r];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // (rm^T * R)(r,c) = sum_k rm[k][r] * R[k][c]
+      p[4 * c + r] = rm[0 + r] * r_old[c] + rm[3 + r] * r_old[3 + c] + rm[6 + r] * r_old[6 + c];
+    }
+}
+
+}  // namespace
+
+void launch_add_layernorm(const __half* x, const __half* y, const float* gamma, const float* beta, __half* out,
+                          long long rows, cudaStream_t s) {
+  if (rows <= 0) return;
+  const int threads = 256;
+  const long long blocks = (rows * 32 + threads - 1) / threads;
+  add_layernorm_kernel<<<(unsigned)blocks, threads, 0, s>>>(x, y, gamma, beta, out, rows);
+}
+
+void launch_token_mean(const __half* x, float* out, int n, cudaStream_t s) {
+  if (n <= 0) return;
+  token_mean_kernel<<<n, 1024, 0, s>>>(x, out);
+}
+
+void launch_small_linear(const float* in, const float* w, const float* b, float* out, int rows, int k, int outs,
+                         cudaStream_t s) {
+  if (rows <= 0) return;
+  dim3 grid((rows + kSLRows - 1) / kSLRows, (outs + 63) / 64);
+  small_linear_kernel<<<grid, 256, sizeof(float) * kSLRows * k, s>>>(in, w, b, out, rows, k, outs);
+}
+
+void launch_cross_attention(const float* qkv, float* out, int n, cudaStream_t s) {
+  if (n <= 0) return;
+  const int warps = 4;
+  cross_attention_kernel<<<(n * 4 + warps - 1) / warps, warps * 32, sizeof(float) * warps * n, s>>>(qkv, out, n);
+}
+
+void launch_argmax_pose(const float* scores, const float* poses, int n, int* best_index, float* best_pose,
+                        cudaStream_t s) {
+  argmax_pose_kernel<<<1, 256, 0, s>>>(scores, poses, n, best_index, best_pose);
+}
+
+void launch_refine_update(const float* mean_t, const float* mean_r, const float* wt, const float* bt,
+                          const float* wr, const float* br, float diameter, float* poses, float* trans_out,
+                          float* rot_out, int n, cudaStream_t s) {
+  if (n <= 0) return;
+  const int threads = 128;
+  refine_update_kernel<<<(n * 32 + threads - 1) / threads, threads, 0, s>>>(mean_t, mean_r, wt, bt, wr, br,
+                                                                           diameter / 2.f, poses, trans_out,
+                                                                           rot_out, n);
+}
+
+}  // namespace fpb

@@ -1,0 +1,35 @@
+// Non-GEMM network operators: attention core, residual LayerNorm, token means, small fp32 heads,
+// pose update and ranking.
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace fpb {
+
+const char* attention_init();
+// qkv: [n_hyp*400, qkv_ld] fp16 with Q | K | V blocks of 4 heads x 128; out: [n_hyp*400, out_ld].
+void launch_attention(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, cudaStream_t s);
+
+// out = LayerNorm(x + y) * gamma + beta over 512 channels, eps 1e-5 (post-LN of
+// nn.TransformerEncoderLayer).  x, y, out: [rows,512] fp16.
+void launch_add_layernorm(const __half* x, const __half* y, const float* gamma, const float* beta,
+                          __half* out, long long rows, cudaStream_t s);
+// mean over the 400 tokens: x [n,400,512] fp16 -> out [n,512] f32
+void launch_token_mean(const __half* x, float* out, int n, cudaStream_t s);
+// out[r,o] = sum_k in[r,k] * w[o,k] + b[o]   (fp32, small shapes)
+void launch_small_linear(const float* in, const float* w, const float* b, float* out, int rows, int k,
+                         int outs, cudaStream_t s);
+// Multi-head attention over a single sequence of n rows: qkv [n,1536] f32 -> out [n,512] f32.
+void launch_cross_attention(const float* qkv, float* out, int n, cudaStream_t s);
+// argmax (first maximum, like thrust::max_element in foundationpose_decoder.cu:24-35) and copy of
+// the winning pose; best_index/best_pose live in device memory.
+void launch_argmax_pose(const float* scores, const float* poses, int n, int* best_index, float* best_pose,
+                        cudaStream_t s);
+// RefinePostProcess (foundationpose.cpp:360-406) on the device: heads = mean tokens x Linear(512,3),
+// then t += trans * d/2, R <- Rodrigues(tanh(rot) * 0.349066)^T R.  mean_t / mean_r: [n,512] f32.
+void launch_refine_update(const float* mean_t, const float* mean_r, const float* wt, const float* bt,
+                          const float* wr, const float* br, float diameter, float* poses, float* trans_out,
+                          float* rot_out, int n, cudaStream_t s);
+
+}  // namespace fpb

@@ -1,0 +1,246 @@
+// Layer graph of the refine / score networks (see network.h, SURVEY.md §2.3 for the structure).
+#include "network.h"
+
+#include <cstdio>
+#include <cstring>
+#include <functional>
+
+#include "common.h"
+#include "net_ops.h"
+
+namespace fpb {
+
+// ------------------------------------------------------------------ weight file
+namespace {
+struct RawEntry {
+  char name[48];
+  uint32_t dtype, ndim, dims[4];
+  uint64_t offset, nbytes;
+};
+static_assert(sizeof(RawEntry) == 48 + 4 + 4 + 16 + 8 + 8, "packed header entry");
+}  // namespace
+
+WeightFile::WeightFile(const std::string& path, int expected_kind) : path_(path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw std::runtime_error("cannot open weight file " + path);
+  std::vector<uint8_t> buf;
+  fseek(f, 0, SEEK_END);
+  const long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  buf.resize(sz > 0 ? sz : 0);
+  const size_t got = fread(buf.data(), 1, buf.size(), f);
+  fclose(f);
+  if (got != buf.size() || buf.size() < 16 || memcmp(buf.data(), "FPB2W001", 8) != 0)
+    throw std::runtime_error("not an FPB2W001 weight file: " + path);
+  uint32_t kind, count;
+  memcpy(&kind, buf.data() + 8, 4);
+  memcpy(&count, buf.data() + 12, 4);
+  if ((int)kind != expected_kind)
+    throw std::runtime_error("weight file " + path + " holds the wrong network kind");
+  if (16 + (size_t)count * sizeof(RawEntry) > buf.size()) throw std::runtime_error("truncated weight file " + path);
+  FPB_CUDA(cudaMalloc(&blob_, buf.size()));
+  FPB_CUDA(cudaMemcpy(blob_, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+  for (uint32_t i = 0; i < count; ++i) {
+    RawEntry e;
+    memcpy(&e, buf.data() + 16 + (size_t)i * sizeof(RawEntry), sizeof(e));
+    if (e.offset + e.nbytes > buf.size() || e.ndim > 4) throw std::runtime_error("corrupt weight file " + path);
+    WeightTensor t;
+    t.dev = static_cast<uint8_t*>(blob_) + e.offset;
+    t.dtype = (int)e.dtype;
+    t.ndim = (int)e.ndim;
+    for (int d = 0; d < 4; ++d) t.dims[d] = (int)e.dims[d];
+    tensors_[std::string(e.name, strnlen(e.name, sizeof(e.name)))] = t;
+  }
+}
+
+WeightFile::~WeightFile() {
+  if (blob_) cudaFree(blob_);
+}
+
+const WeightTensor& WeightFile::get(const std::string& name, int dtype, int d0, int d1) const {
+  auto it = tensors_.find(name);
+  if (it == tensors_.end()) throw std::runtime_error("weight file " + path_ + " has no tensor '" + name + "'");
+  const WeightTensor& t = it->second;
+  if (t.dtype != dtype || t.dims[0] != d0 || (d1 >= 0 && t.dims[1] != d1)) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "tensor '%s' has dtype %d dims [%d,%d], expected dtype %d dims [%d,%d]",
+             name.c_str(), t.dtype, t.dims[0], t.dims[1], dtype, d0, d1);
+    throw std::runtime_error(msg);
+  }
+  return t;
+}
+
+// ------------------------------------------------------------------ arena
+Arena::Arena(int max_hyps) : cap(max_hyps) {
+  const size_t n = (size_t)max_hyps;
+  struct Item { void** p; size_t bytes; };
+  const size_t tok = n * 400 * 512 * 2;
+  std::vector<Item> items = {
+      {(void**)&packed, (2 * n * (size_t)kPackImageElems + (size_t)kStemPitch * kPackC) * 2},
+      {(void**)&stem, 2 * n * 80 * 80 * 64 * 2},
+      {(void**)&a0, 2 * n * 40 * 40 * 128 * 2}, {(void**)&a1, 2 * n * 40 * 40 * 128 * 2},
+      {(void**)&a2, 2 * n * 40 * 40 * 128 * 2},
+      {(void**)&c0, n * 40 * 40 * 256 * 2}, {(void**)&c1, n * 40 * 40 * 256 * 2}, {(void**)&c2, n * 40 * 40 * 256 * 2},
+      {(void**)&d0, tok}, {(void**)&d1, tok}, {(void**)&d2, tok},
+      {(void**)&qkv, 3 * tok}, {(void**)&att, tok}, {(void**)&proj, tok}, {(void**)&x1, tok},
+      {(void**)&ff1, tok}, {(void**)&ff2, tok}, {(void**)&x2, tok},
+      {(void**)&mean_t, n * 512 * 4}, {(void**)&mean_r, n * 512 * 4},
+  };
+  size_t total = 0;
+  for (auto& it : items) total += (it.bytes + 1023) / 1024 * 1024;
+  FPB_CUDA(cudaMalloc(&blob, total));
+  bytes = total;
+  size_t off = 0;
+  for (auto& it : items) {
+    *it.p = static_cast<uint8_t*>(blob) + off;
+    off += (it.bytes + 1023) / 1024 * 1024;
+  }
+  // the stem reads zero pad pixels that no kernel ever writes
+  FPB_CUDA(cudaMemset(packed, 0, (2 * n * (size_t)kPackImageElems + (size_t)kStemPitch * kPackC) * 2));
+}
+
+Arena::~Arena() {
+  if (blob) cudaFree(blob);
+}
+
+// ------------------------------------------------------------------ network
+struct Network::Plan {
+  std::vector<std::function<void(cudaStream_t)>> steps;
+  double flops = 0;
+};
+
+Network::Network(NetKind kind, const std::string& weight_path, Arena* arena)
+    : kind_(kind), w_(new WeightFile(weight_path, (int)kind)), arena_(arena) {
+  if (const char* e = conv_gemm_init()) throw std::runtime_error(e);
+  if (const char* e = attention_init()) throw std::runtime_error(e);
+  flops_per_hyp_ = plan(1).flops;
+}
+
+Network::~Network() = default;
+
+namespace {
+void add_gemm(std::vector<std::function<void(cudaStream_t)>>& steps, double* flops, const ConvGemmDesc& d) {
+  ConvGemmPlan pl;
+  if (const char* e = build_conv_gemm(d, &pl)) throw std::runtime_error(e);
+  *flops += pl.flops;
+  steps.push_back([pl](cudaStream_t s) { FPB_CUDA(launch_conv_gemm(pl, s)); });
+}
+}  // namespace
+
+void Network::add_backbone(Plan& p, int n) {
+  Arena& A = *arena_;
+  const WeightFile& W = *w_;
+  const int n2 = 2 * n;
+  {  // stem: 7x7 s2, (6 -> 64), packed input -> phase-split 80x80x64
+    ConvGemmDesc d;
+    d.in = A.packed;
+    d.n_img = n2; d.planes = 2; d.in_h = 80; d.in_w = 80; d.cin = 64;
+    const long long pitch_b = (long long)kStemPitch * kPackC * 2;
+    d.stride_w = 32; d.stride_plane = pitch_b; d.stride_h = 2 * pitch_b; d.stride_img = kCrop * pitch_b;
+    d.out_h = 80; d.out_w = 80; d.bw = 16; d.bh = 8; d.bn = 1;
+    taps_stem7_rows(&d);
+    d.weight = W.f16("enc.stem.w", 64, 448); d.cout = 64; d.bias = W.f32("enc.stem.b", 64);
+    d.out = A.stem; d.relu = true; d.out_phase_split = true;
+    add_gemm(p.steps, &p.flops, d);
+    // count the stem at its algorithmic size (7*7*6 MACs per output), not the padded K of 448
+    p.flops -= 2.0 * n2 * 80 * 80 * 64 * (448 - 294);
+  }
+  auto conv = [&](const __half* in, int imgs, int hw, int cin, bool s2, const std::string& name, int cout,
+                  __half* out, const __half* res, int res_ld, bool phase_out, int out_ld, int img_mod, int half_coff,
+                  const float* post) {
+    ConvGemmDesc d;
+    d.in = in; d.n_img = imgs; d.cin = cin;
+    const int ho = s2 ? hw / 2 : hw;
+    d.in_h = ho; d.in_w = ho; d.planes = s2 ? 4 : 1;
+    d.out_h = ho; d.out_w = ho;
+    if (ho % 8 == 0) { d.bw = 8; d.bh = 8; d.bn = 2; } else { d.bw = 4; d.bh = 4; d.bn = 8; }
+    if (s2) taps_3x3_s2_phase(&d); else taps_3x3_s1(&d);
+    d.weight = W.f16(name + ".w", cout, 9 * cin); d.cout = cout; d.bias = W.f32(name + ".b", cout);
+    d.residual = res; d.res_ld = res_ld; d.post_add = post;
+    d.out = out; d.relu = true; d.out_phase_split = phase_out; d.out_ld = out_ld; d.img_mod = img_mod;
+    d.half_coff = half_coff;
+    add_gemm(p.steps, &p.flops, d);
+  };
+  conv(A.stem, n2, 80, 64, true, "enc.a1", 128, A.a0, nullptr, 0, false, 0, 0, 0, nullptr);
+  conv(A.a0, n2, 40, 128, false, "enc.a.r0.c1", 128, A.a1, nullptr, 0, false, 0, 0, 0, nullptr);
+  conv(A.a1, n2, 40, 128, false, "enc.a.r0.c2", 128, A.a2, A.a0, 128, false, 0, 0, 0, nullptr);
+  conv(A.a2, n2, 40, 128, false, "enc.a.r1.c1", 128, A.a1, nullptr, 0, false, 0, 0, 0, nullptr);
+  // last encodeA layer writes a || b side by side: image i < n -> channels [0,128), i >= n -> [128,256)
+  conv(A.a1, n2, 40, 128, false, "enc.a.r1.c2", 128, A.c0, A.a2, 128, false, 256, n, 128, nullptr);
+  conv(A.c0, n, 40, 256, false, "enc.ab.r0.c1", 256, A.c1, nullptr, 0, false, 0, 0, 0, nullptr);
+  conv(A.c1, n, 40, 256, false, "enc.ab.r0.c2", 256, A.c2, A.c0, 256, false, 0, 0, 0, nullptr);
+  conv(A.c2, n, 40, 256, false, "enc.ab.r1.c1", 256, A.c1, nullptr, 0, false, 0, 0, 0, nullptr);
+  conv(A.c1, n, 40, 256, false, "enc.ab.r1.c2", 256, A.c0, A.c2, 256, true, 0, 0, 0, nullptr);
+  conv(A.c0, n, 40, 256, true, "enc.ab.down", 512, A.d0, nullptr, 0, false, 0, 0, 0, nullptr);
+  conv(A.d0, n, 20, 512, false, "enc.ab.r2.c1", 512, A.d1, nullptr, 0, false, 0, 0, 0, nullptr);
+  conv(A.d1, n, 20, 512, false, "enc.ab.r2.c2", 512, A.d2, A.d0, 512, false, 0, 0, 0, nullptr);
+  conv(A.d2, n, 20, 512, false, "enc.ab.r3.c1", 512, A.d1, nullptr, 0, false, 0, 0, 0, nullptr);
+  // tokens (+ positional table) land in d0: [n, 400, 512]
+  conv(A.d1, n, 20, 512, false, "enc.ab.r3.c2", 512, A.d0, A.d2, 512, false, 0, 0, 0, W.f32("pos.table", 400, 512));
+}
+
+namespace {
+ConvGemmDesc linear_desc(const __half* in, long long rows, int k, const __half* w, const float* b, int outs,
+                         __half* out, bool relu) {
+  ConvGemmDesc d;
+  d.in = in; d.n_img = 1; d.planes = 1; d.in_h = 1; d.in_w = (int)rows; d.cin = k;
+  d.out_h = 1; d.out_w = (int)rows; d.bw = 128; d.bh = 1; d.bn = 1;
+  d.num_taps = 1;
+  d.weight = w; d.cout = outs; d.bias = b; d.out = out; d.relu = relu;
+  return d;
+}
+}  // namespace
+
+void Network::add_encoder_layer(Plan& p, int n, const std::string& h, float* mean_out) {
+  Arena& A = *arena_;
+  const WeightFile& W = *w_;
+  const long long rows = (long long)n * 400;
+  add_gemm(p.steps, &p.flops, linear_desc(A.d0, rows, 512, W.f16(h + ".qkv.w", 1536, 512), W.f32(h + ".qkv.b", 1536), 1536, A.qkv, false));
+  p.steps.push_back([&A, n](cudaStream_t s) { launch_attention(A.qkv, A.att, n, 1536, 512, s); });
+  p.flops += 2.0 * n * 4 * 2 * 400.0 * 400.0 * 128.0;
+  add_gemm(p.steps, &p.flops, linear_desc(A.att, rows, 512, W.f16(h + ".out.w", 512, 512), W.f32(h + ".out.b", 512), 512, A.proj, false));
+  const float *g1 = W.f32(h + ".ln1.g", 512), *b1 = W.f32(h + ".ln1.b", 512);
+  p.steps.push_back([&A, rows, g1, b1](cudaStream_t s) { launch_add_layernorm(A.d0, A.proj, g1, b1, A.x1, rows, s); });
+  add_gemm(p.steps, &p.flops, linear_desc(A.x1, rows, 512, W.f16(h + ".ff1.w", 512, 512), W.f32(h + ".ff1.b", 512), 512, A.ff1, true));
+  add_gemm(p.steps, &p.flops, linear_desc(A.ff1, rows, 512, W.f16(h + ".ff2.w", 512, 512), W.f32(h + ".ff2.b", 512), 512, A.ff2, false));
+  const float *g2 = W.f32(h + ".ln2.g", 512), *b2 = W.f32(h + ".ln2.b", 512);
+  p.steps.push_back([&A, rows, g2, b2](cudaStream_t s) { launch_add_layernorm(A.x1, A.ff2, g2, b2, A.x2, rows, s); });
+  p.steps.push_back([&A, n, mean_out](cudaStream_t s) { launch_token_mean(A.x2, mean_out, n, s); });
+  p.flops += 2.0 * n * 512 * 3;  // Linear(512,3) on the token mean
+}
+
+Network::Plan& Network::plan(int n) {
+  auto it = plans_.find(n);
+  if (it != plans_.end()) return *it->second;
+  if (n < 1 || n > arena_->cap) throw std::invalid_argument("network: hypothesis count exceeds the session capacity");
+  std::unique_ptr<Plan> p(new Plan);
+  add_backbone(*p, n);
+  Arena& A = *arena_;
+  if (kind_ == NetKind::kRefiner) {
+    add_encoder_layer(*p, n, "trans", A.mean_t);
+    add_encoder_layer(*p, n, "rot", A.mean_r);
+  } else {
+    const WeightFile& W = *w_;
+    const long long rows = (long long)n * 400;
+    add_gemm(p->steps, &p->flops, linear_desc(A.d0, rows, 512, W.f16("att.qkv.w", 1536, 512), W.f32("att.qkv.b", 1536), 1536, A.qkv, false));
+    p->steps.push_back([&A, n](cudaStream_t s) { launch_attention(A.qkv, A.att, n, 1536, 512, s); });
+    p->flops += 2.0 * n * 4 * 2 * 400.0 * 400.0 * 128.0;
+    p->steps.push_back([&A, n](cudaStream_t s) { launch_token_mean(A.att, A.mean_t, n, s); });
+    // out_proj is applied to the token mean by the session (it commutes with the mean); counted
+    // here at the size the reference graph runs it (per token), like the reference FLOP model
+    p->flops += 2.0 * rows * 512 * 512;
+  }
+  p->flops /= n;
+  Plan& ref = *p;
+  plans_[n] = std::move(p);
+  return ref;
+}
+
+void Network::forward(int n, cudaStream_t s) {
+  Plan& p = plan(n);
+  for (auto& st : p.steps) st(s);
+}
+
+int Network::launches_per_forward(int n) { return (int)plan(n).steps.size(); }
+
+}  // namespace fpb

@@ -1,0 +1,83 @@
+// Refine / score networks as sequences of tcgen05 implicit-GEMM layers and small fused operators.
+// Replaces the two TensorRT engines behind BaseInferCore::SyncInfer in the reference
+// (easy_deploy_tool/deploy_core/src/base_infer_core.cpp:33-41, inference_core/trt_core/src/trt_core.cpp:323-371).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "conv_gemm.h"
+#include "preprocess.h"
+
+namespace fpb {
+
+struct WeightTensor {
+  void* dev = nullptr;
+  int dtype = 0;  // 0 = f16, 1 = f32
+  int ndim = 0;
+  int dims[4] = {1, 1, 1, 1};
+};
+
+// Flat weight file (format: foundationpose_cpp_b200/weights.py) resident in device memory.
+class WeightFile {
+ public:
+  WeightFile(const std::string& path, int expected_kind);
+  ~WeightFile();
+  const WeightTensor& get(const std::string& name, int dtype, int d0, int d1 = -1) const;
+  const __half* f16(const std::string& name, int d0, int d1 = -1) const {
+    return static_cast<const __half*>(get(name, 0, d0, d1).dev);
+  }
+  const float* f32(const std::string& name, int d0, int d1 = -1) const {
+    return static_cast<const float*>(get(name, 1, d0, d1).dev);
+  }
+
+ private:
+  std::map<std::string, WeightTensor> tensors_;
+  void* blob_ = nullptr;
+  std::string path_;
+};
+
+// Activation storage shared by both networks (they never run concurrently).
+struct Arena {
+  int cap = 0;  // hypotheses
+  __half *packed = nullptr, *stem = nullptr, *a0 = nullptr, *a1 = nullptr, *a2 = nullptr, *c0 = nullptr,
+         *c1 = nullptr, *c2 = nullptr, *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *qkv = nullptr,
+         *att = nullptr, *proj = nullptr, *x1 = nullptr, *ff1 = nullptr, *ff2 = nullptr, *x2 = nullptr;
+  float *mean_t = nullptr, *mean_r = nullptr;
+  void* blob = nullptr;
+  size_t bytes = 0;
+  explicit Arena(int max_hyps);
+  ~Arena();
+};
+
+enum class NetKind { kRefiner = 0, kScorer = 1 };
+
+struct Step;  // one launch of the forward sequence
+
+class Network {
+ public:
+  Network(NetKind kind, const std::string& weight_path, Arena* arena);
+  ~Network();
+  // Runs the network on hypotheses [0,n) of arena->packed (render images 0..n-1, observed n..2n-1).
+  // Refiner: leaves token means in arena->mean_t / mean_r.  Scorer: leaves the token mean of the
+  // self-attention output (before out_proj) in arena->mean_t.
+  void forward(int n, cudaStream_t s);
+  double flops_per_hypothesis() const { return flops_per_hyp_; }
+  int launches_per_forward(int n);
+  const WeightFile& weights() const { return *w_; }
+
+ private:
+  struct Plan;
+  Plan& plan(int n);
+  void add_backbone(Plan& p, int n);
+  void add_encoder_layer(Plan& p, int n, const std::string& head, float* mean_out);
+  NetKind kind_;
+  std::unique_ptr<WeightFile> w_;
+  Arena* arena_;
+  std::map<int, std::unique_ptr<Plan>> plans_;
+  double flops_per_hyp_ = 0;
+};
+
+}  // namespace fpb

@@ -1,0 +1,652 @@
+// Preprocessing kernels of the Register/Track hot path (see preprocess.h).
+// Reference behaviour restated per kernel (paths relative to detection_6d_foundationpose/src/).
+// This translation unit is compiled with -fmad=false: expressions round exactly as written.
+#include "preprocess.h"
+
+#include <cfloat>
+
+namespace fpb {
+
+namespace {
+
+constexpr float kMinDepth = 0.001f;  // foundationpose_render.hpp:26
+constexpr float kMaxDepth = 4.0f;    // foundationpose_render.hpp:27 (applied to normalised coords)
+constexpr float kZFar = 100.0f;      // foundationpose_sampling.cu.hpp defaults
+
+// ------------------------------------------------------------------ depth -> xyz
+// foundationpose_utils.cu:3-32.  Invalid pixels are written as zero (the reference leaves them
+// uninitialised; they are zeroed downstream by the z < min_depth test either way).
+__global__ void depth_to_xyz_kernel(const float* __restrict__ depth, float* __restrict__ xyz, int h,
+                                    int w, float fx, float fy, float cx, float cy) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= h * w) return;
+  const int row = idx / w, col = idx - row * w;
+  const float d = depth[idx];
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (!(d < kMinDepth)) {
+    x = ((float)col - cx) * d / fx;
+    y = ((float)row - cy) * d / fy;
+    z = d;
+  }
+  xyz[3 * idx + 0] = x;
+  xyz[3 * idx + 1] = y;
+  xyz[3 * idx + 2] = z;
+}
+
+// ------------------------------------------------------------------ sampler depth filters
+// foundationpose_sampling.cu:21-82 (radius 2, 1 mm, ratio 0.8, zfar 100).
+__global__ void erode_depth_kernel(const float* __restrict__ depth, float* __restrict__ out, int H,
+                                   int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y * blockDim.y + threadIdx.y;
+  if (w >= W || h >= H) return;
+  const float d_ori = depth[h * W + w];
+  if (d_ori < 0.1f || d_ori >= kZFar) {
+    out[h * W + w] = 0.f;
+    return;
+  }
+  float bad = 0.f, total = 0.f;
+  for (int u = w - 2; u <= w + 2; ++u) {
+    if (u < 0 || u >= W) continue;
+    for (int v = h - 2; v <= h + 2; ++v) {
+      if (v < 0 || v >= H) continue;
+      const float cur = depth[v * W + u];
+      total += 1.f;
+      if (cur < 0.1f || cur >= kZFar || fabsf(cur - d_ori) > 0.001f) bad += 1.f;
+    }
+  }
+  out[h * W + w] = (bad / total) > 0.8f ? 0.f : d_ori;
+}
+
+// foundationpose_sampling.cu:84-164 (radius 2, sigmaD 2, sigmaR 1e5).
+__global__ void bilateral_depth_kernel(const float* __restrict__ depth, float* __restrict__ out,
+                                       int H, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y * blockDim.y + threadIdx.y;
+  if (w >= W || h >= H) return;
+  float mean = 0.f;
+  int num_valid = 0;
+  for (int u = w - 2; u <= w + 2; ++u) {
+    if (u < 0 || u >= W) continue;
+    for (int v = h - 2; v <= h + 2; ++v) {
+      if (v < 0 || v >= H) continue;
+      const float cur = depth[v * W + u];
+      if (cur >= 0.1f && cur < kZFar) {
+        ++num_valid;
+        mean += cur;
+      }
+    }
+  }
+  if (num_valid == 0) {
+    out[h * W + w] = 0.f;
+    return;
+  }
+  mean /= (float)num_valid;
+  const float center = depth[h * W + w];
+  float sum_w = 0.f, sum = 0.f;
+  const float sigma_d = 2.f, sigma_r = 100000.f;
+  for (int u = w - 2; u <= w + 2; ++u) {
+    if (u < 0 || u >= W) continue;
+    for (int v = h - 2; v <= h + 2; ++v) {
+      if (v < 0 || v >= H) continue;
+      const float cur = depth[v * W + u];
+      if (cur >= 0.1f && cur < kZFar && fabsf(cur - mean) < 0.01f) {
+        const float wgt = expf(-((float)((u - w) * (u - w) + (v - h) * (v - h))) / (2.f * sigma_d * sigma_d) -
+                               (center - cur) * (center - cur) / (2.f * sigma_r * sigma_r));
+        sum_w += wgt;
+        sum += wgt * cur;
+      }
+    }
+  }
+  out[h * W + w] = (sum_w > 0.f) ? sum / sum_w : 0.f;
+}
+
+// ------------------------------------------------------------------ translation guess
+// GuessTranslation, foundationpose_sampling.cpp:250-298, as one 1024-thread CTA: mask bounding
+// box, then an exact median of the valid depths by 4-pass radix select on the float bit patterns
+// (depths are positive, so the patterns order like the values; the reference uses std::sort).
+__device__ __forceinline__ bool valid_px(const float* d, const uint8_t* m, int i, uint32_t* key) {
+  if (m[i] == 0) return false;
+  const float v = d[i];
+  if (!(v >= kMinDepth)) return false;
+  *key = __float_as_uint(v);
+  return true;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+guess_translation_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ mask, int h,
+                         int w, Intrinsics K, float* __restrict__ center, int* __restrict__ status) {
+  __shared__ unsigned hist[256];
+  __shared__ int s_umin, s_umax, s_vmin, s_vmax;
+  __shared__ unsigned s_n, s_prefix, s_rank, s_cnt_less, s_max_less;
+  const int tid = threadIdx.x;
+  const int npx = h * w;
+  if (tid == 0) {
+    s_umin = INT_MAX; s_vmin = INT_MAX; s_umax = -1; s_vmax = -1;
+    s_n = 0; s_cnt_less = 0; s_max_less = 0;
+  }
+  __syncthreads();
+  int umin = INT_MAX, umax = -1, vmin = INT_MAX, vmax = -1;
+  unsigned n = 0;
+  for (int i = tid; i < npx; i += blockDim.x) {
+    if (mask[i]) {
+      const int v = i / w, u = i - v * w;
+      umin = min(umin, u); umax = max(umax, u); vmin = min(vmin, v); vmax = max(vmax, v);
+      uint32_t key;
+      if (valid_px(depth, mask, i, &key)) ++n;
+    }
+  }
+  atomicMin(&s_umin, umin); atomicMax(&s_umax, umax);
+  atomicMin(&s_vmin, vmin); atomicMax(&s_vmax, vmax);
+  atomicAdd(&s_n, n);
+  __syncthreads();
+  if (s_umax < 0) {
+    if (tid == 0) atomicOr(status, kStatusEmptyMask);
+    return;
+  }
+  const unsigned total = s_n;
+  if (total == 0) {
+    if (tid == 0) atomicOr(status, kStatusNoDepth);
+    return;
+  }
+  if (tid == 0) {
+    s_prefix = 0;
+    s_rank = total / 2;  // 0-based rank of the upper median
+  }
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned himask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = tid; i < npx; i += blockDim.x) {
+      uint32_t key;
+      if (valid_px(depth, mask, i, &key) && (key & himask) == prefix)
+        atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned r = s_rank, b = 0;
+      for (; b < 256; ++b) {
+        if (r < hist[b]) break;
+        r -= hist[b];
+      }
+      s_rank = r;
+      s_prefix = prefix | (b << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t hi_key = s_prefix;
+  unsigned cnt_less = 0, max_less = 0;
+  for (int i = tid; i < npx; i += blockDim.x) {
+    uint32_t key;
+    if (valid_px(depth, mask, i, &key) && key < hi_key) {
+      ++cnt_less;
+      max_less = max(max_less, key);
+    }
+  }
+  atomicAdd(&s_cnt_less, cnt_less);
+  atomicMax(&s_max_less, max_less);
+  __syncthreads();
+  if (tid == 0) {
+    const float hi = __uint_as_float(hi_key);
+    float zc = hi;
+    if ((total & 1u) == 0) {
+      const float lo = (s_cnt_less == total / 2) ? __uint_as_float(s_max_less) : hi;
+      zc = (lo + hi) / 2.f;
+    }
+    const float uc = (float)(s_umin + s_umax) / 2.f;
+    const float vc = (float)(s_vmin + s_vmax) / 2.f;
+    for (int r = 0; r < 3; ++r)
+      center[r] = ((K.kinv[3 * r] * uc + K.kinv[3 * r + 1] * vc) + K.kinv[3 * r + 2]) * zc;
+  }
+}
+
+// GetHypPoses step 4, foundationpose_sampling.cpp:388-391.
+__global__ void fill_hypotheses_kernel(const float* __restrict__ grid, const float* __restrict__ center,
+                                       float* __restrict__ poses, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 16) return;
+  const int e = i & 15;
+  float v = grid[i];
+  if (e >= 12 && e < 15) v = center[e - 12];
+  poses[i] = v;
+}
+
+// ------------------------------------------------------------------ per-pose setup
+__device__ __forceinline__ void mat4_mul(const float* a, const float* b, float* out) {
+  // row-major, k-sum left to right (matches oracle/fp_oracle.py:_mat4_mul)
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float s = a[4 * i] * b[j];
+      for (int k = 1; k < 4; ++k) s = s + a[4 * i + k] * b[4 * k + j];
+      out[4 * i + j] = s;
+    }
+}
+
+// ComputeCropWindowTF / ComputeTF / ConstructBBox2D / ProjectMatrixFromIntrinsics + the matrix
+// product of GeneratePoseClipOnCUDA (foundationpose_render.cpp:25-75,123-186,588-593) and the
+// zoom constants of generate_pose_clip_kernel (foundationpose_render.cu:382-386), one thread per pose.
+__global__ void pose_setup_kernel(const float* __restrict__ poses, int n, Intrinsics K, float diameter,
+                                  float crop_ratio, PoseAux* __restrict__ aux) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = poses + 16 * i;  // column-major
+  PoseAux a;
+  float pose_rm[16];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) pose_rm[4 * r + c] = p[4 * c + r];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) a.rot[3 * r + c] = pose_rm[4 * r + c];
+    a.t[r] = pose_rm[4 * r + 3];
+  }
+  // crop window
+  const float rad3 = diameter * crop_ratio / 2.f;
+  const float tx = a.t[0], ty = a.t[1], tz = a.t[2];
+  const float u0 = ((K.fx * tx + K.k01 * ty) + K.cx * tz) / tz;
+  const float v0 = (K.fy * ty + K.cy * tz) / tz;
+  float dv_max = 0.f;  // point 0 contributes v0 - v0 = 0
+  {
+    const float vy_p = (K.fy * (ty + rad3) + K.cy * tz) / tz;
+    const float vy_m = (K.fy * (ty - rad3) + K.cy * tz) / tz;
+    dv_max = fmaxf(dv_max, v0 - v0);
+    dv_max = fmaxf(dv_max, vy_p - v0);
+    dv_max = fmaxf(dv_max, vy_m - v0);
+  }
+  const float radius = fabsf(dv_max);
+  const float left = roundf(u0 - radius), right = roundf(u0 + radius);
+  const float top = roundf(v0 - radius), bottom = roundf(v0 + radius);
+  const float sx = (float)kCrop / (right - left), sy = (float)kCrop / (bottom - top);
+  const float tf02 = sx * (-left), tf12 = sy * (-top);
+  a.tf[0] = sx; a.tf[1] = 0.f; a.tf[2] = tf02;
+  a.tf[3] = 0.f; a.tf[4] = sy; a.tf[5] = tf12;
+  a.tf[6] = 0.f; a.tf[7] = 0.f; a.tf[8] = 1.f;
+  a.inv_sx = 1.f / sx;
+  a.inv_sy = 1.f / sy;
+  a.left = left;
+  a.top = top;
+  // bbox2d = tf^-1 * {(0,0), (W-1,H-1)}
+  const float bl = -tf02 / sx, bt = -tf12 / sy;
+  a.bbox[0] = bl;
+  a.bbox[1] = bt;
+  a.bbox[2] = (float)(kCrop - 1) / sx + bl;
+  a.bbox[3] = (float)(kCrop - 1) / sy + bt;
+  // clip-space zoom
+  const float fh = (float)K.img_h, fw = (float)K.img_w;
+  const float l = a.bbox[0], t = fh - a.bbox[1], r = a.bbox[2], b = fh - a.bbox[3];
+  a.a00 = fw / (r - l);
+  a.a11 = fh / (t - b);
+  a.a30 = (fw - r - l) / (r - l);
+  a.a31 = (fh - t - b) / (t - b);
+  // MVP
+  const float gl[16] = {1, 0, 0, 0, 0, -1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1};
+  float tmp[16];
+  mat4_mul(gl, pose_rm, tmp);
+  mat4_mul(K.proj, tmp, a.mvp);
+  aux[i] = a;
+}
+
+// ------------------------------------------------------------------ fused render
+constexpr int kRenderThreads = 512;
+constexpr unsigned kDepthMin = 2200u << 3;
+constexpr unsigned kDepthMax = 0xFFFFFFFFu - (2200u << 3);
+
+struct ClipV {
+  float x, y, z, w;
+};
+
+__device__ __forceinline__ ClipV clip_vertex(const PoseAux& a, const float* __restrict__ v) {
+  // generate_pose_clip_kernel, foundationpose_render.cu:388-397
+  const float x = v[0], y = v[1], z = v[2];
+  const float tx = ((a.mvp[0] * x + a.mvp[1] * y) + a.mvp[2] * z) + a.mvp[3];
+  const float ty = ((a.mvp[4] * x + a.mvp[5] * y) + a.mvp[6] * z) + a.mvp[7];
+  const float tz = ((a.mvp[8] * x + a.mvp[9] * y) + a.mvp[10] * z) + a.mvp[11];
+  const float tw = ((a.mvp[12] * x + a.mvp[13] * y) + a.mvp[14] * z) + a.mvp[15];
+  ClipV c;
+  c.x = tx * a.a00 + tw * a.a30;
+  c.y = ty * a.a11 + tw * a.a31;
+  c.z = tz;
+  c.w = tw;
+  return c;
+}
+
+__device__ __forceinline__ int snap(float v) {
+  int r;
+  asm("cvt.rni.sat.s32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ int min3(int a, int b, int c) { return min(a, min(b, c)); }
+__device__ __forceinline__ int max3(int a, int b, int c) { return max(a, max(b, c)); }
+
+// Integer depth plane, cudaraster Util.inl:184-210.
+__device__ __forceinline__ void setup_pleq(float z0, float z1, float z2, int v0x, int v0y, int d1x,
+                                           int d1y, int d2x, int d2y, float area_rcp, unsigned* pl) {
+  const float mx = fmaxf(fmaxf(z0, z1), z2);
+  const int sh = min(max((__float_as_int(mx) >> 23) - (127 + 22), 0), 8);
+  const int t0 = (int)((unsigned)z0 >> sh);
+  const int t1 = (int)((unsigned)z1 >> sh) - t0;
+  const int t2 = (int)((unsigned)z2 >> sh) - t0;
+  const unsigned rcp_mant = (__float_as_int(area_rcp) & 0x007FFFFF) | 0x00800000;
+  const int rcp_shift = (23 + 127) - (__float_as_int(area_rcp) >> 23);
+  const long long xc = ((long long)t1 * d2y - (long long)t2 * d1y) * (long long)rcp_mant;
+  const long long yc = ((long long)t2 * d1x - (long long)t1 * d2x) * (long long)rcp_mant;
+  pl[0] = (unsigned)(xc >> (rcp_shift - (sh + 4)));
+  pl[1] = (unsigned)(yc >> (rcp_shift - (sh + 4)));
+  const int cx = (v0x * 2 + min3(d1x, d2x, 0) + max3(d1x, d2x, 0)) >> 5;
+  const int cy = (v0y * 2 + min3(d1y, d2y, 0) + max3(d1y, d2y, 0)) >> 5;
+  const int vcx = v0x - cx * 16;
+  const int vcy = v0y - cy * 16;
+  unsigned z = (unsigned)t0 << sh;
+  z -= (unsigned)(((xc >> 13) * vcx + (yc >> 13) * vcy) >> (rcp_shift - (sh + 13)));
+  z -= pl[0] * (unsigned)cx + pl[1] * (unsigned)cy;
+  pl[2] = z;
+}
+
+// One CTA per hypothesis.  Phase 1: every thread takes triangles, does cudaraster's triangle
+// setup (TriangleSetup.inl fast path) and resolves visibility with a 64-bit atomicMin on a
+// shared-memory z-buffer whose key is (u32 depth << 32) | ~triangle, i.e. nearest wins and on equal
+// depth the later triangle wins (FineRaster.inl:152-172,338-351).  Phase 2: per pixel, nvdiffrast's
+// barycentrics / interpolation / texture (rasterize.cu:55-89, interpolate.cu:46-76,
+// texture.cu:19-96), the reference's shading (foundationpose_render.cu:459-501), vertical flip
+// (foundationpose_render.cpp:676-680), normalisation and packing (foundationpose_render.cu:61-140).
+__global__ void __launch_bounds__(kRenderThreads, 1)
+render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, __half* __restrict__ packed,
+              int img0, int32_t* __restrict__ rast_id_debug, int* __restrict__ status) {
+  extern __shared__ unsigned long long zbuf[];  // [160*160]
+  __shared__ PoseAux a;
+  const int pose = blockIdx.x;
+  if (threadIdx.x < sizeof(PoseAux) / 4)
+    reinterpret_cast<float*>(&a)[threadIdx.x] = reinterpret_cast<const float*>(aux_all + pose)[threadIdx.x];
+  for (int i = threadIdx.x; i < kCrop * kCrop; i += blockDim.x) zbuf[i] = ~0ull;
+  __syncthreads();
+
+  constexpr int W = kCrop, H = kCrop;
+  const float vs = (float)(W << 3);
+  constexpr int bias = (W - 1) << 3;  // sample x of pixel px = px*16 - bias
+  bool clip_path = false;
+  for (int t = threadIdx.x; t < mesh.num_faces; t += blockDim.x) {
+    const int i0 = mesh.faces[3 * t], i1 = mesh.faces[3 * t + 1], i2 = mesh.faces[3 * t + 2];
+    if ((unsigned)i0 >= (unsigned)mesh.num_vertices || (unsigned)i1 >= (unsigned)mesh.num_vertices ||
+        (unsigned)i2 >= (unsigned)mesh.num_vertices)
+      continue;
+    const ClipV A = clip_vertex(a, mesh.vertices + 3 * i0);
+    const ClipV B = clip_vertex(a, mesh.vertices + 3 * i1);
+    const ClipV C = clip_vertex(a, mesh.vertices + 3 * i2);
+    if ((A.w < fabsf(A.x)) | (A.w < fabsf(A.y)) | (A.w < fabsf(A.z))) {
+      if (((A.w < +A.x) & (B.w < +B.x) & (C.w < +C.x)) | ((A.w < -A.x) & (B.w < -B.x) & (C.w < -C.x)) |
+          ((A.w < +A.y) & (B.w < +B.y) & (C.w < +C.y)) | ((A.w < -A.y) & (B.w < -B.y) & (C.w < -C.y)) |
+          ((A.w < +A.z) & (B.w < +B.z) & (C.w < +C.z)) | ((A.w < -A.z) & (B.w < -B.z) & (C.w < -C.z)))
+        continue;
+    }
+    if (!((A.w >= fabsf(A.z)) & (B.w >= fabsf(B.z)) & (C.w >= fabsf(C.z)))) {
+      clip_path = true;  // cudaraster would clip this triangle against the near/far plane
+      continue;
+    }
+    float rw0 = 1.0f / A.w, rw1 = 1.0f / B.w, rw2 = 1.0f / C.w;
+    int p0x = snap(A.x * rw0 * vs), p0y = snap(A.y * rw0 * vs);
+    int p1x = snap(B.x * rw1 * vs), p1y = snap(B.y * rw1 * vs);
+    int p2x = snap(C.x * rw2 * vs), p2y = snap(C.y * rw2 * vs);
+    const int lox = min3(p0x, p1x, p2x), loy = min3(p0y, p1y, p2y);
+    const int hix = max3(p0x, p1x, p2x), hiy = max3(p0y, p1y, p2y);
+    if (!(min(lox, loy) >= -32768 && max(hix, hiy) <= 32767 &&
+          max(hix, hiy) - min(lox, loy) <= (1 << 15) - 1)) {
+      clip_path = true;
+      continue;
+    }
+    int d1x = p1x - p0x, d1y = p1y - p0y, d2x = p2x - p0x, d2y = p2y - p0y;
+    int area = d1x * d2y - d1y * d2x;
+    if (area == 0) continue;
+    float z0 = A.z, z1 = B.z, z2 = C.z;
+    if (area < 0) {
+      int ti;
+      float tf;
+      ti = d1x; d1x = d2x; d2x = ti;
+      ti = d1y; d1y = d2y; d2y = ti;
+      ti = p1x; p1x = p2x; p2x = ti;
+      ti = p1y; p1y = p2y; p2y = ti;
+      tf = z1; z1 = z2; z2 = tf;
+      tf = rw1; rw1 = rw2; rw2 = tf;
+      area = -area;
+    }
+    const float zcoef = (float)(kDepthMax - kDepthMin) * 0.5f;
+    const float zbias = (float)(kDepthMax + kDepthMin) * 0.5f;
+    const float zv0 = fmaf(z0 * zcoef, rw0, zbias), zv1 = fmaf(z1 * zcoef, rw1, zbias),
+                zv2 = fmaf(z2 * zcoef, rw2, zbias);
+    unsigned pl[3];
+    setup_pleq(zv0, zv1, zv2, p0x + (W << 3) - 8, p0y + (H << 3) - 8, d1x, d1y, d2x, d2y,
+               1.0f / (float)area, pl);
+    const int px0 = max((lox + bias + 15) >> 4, 0), px1 = min((hix + bias) >> 4, W - 1);
+    const int py0 = max((loy + bias + 15) >> 4, 0), py1 = min((hiy + bias) >> 4, H - 1);
+    const int e0x = d1x, e0y = d1y, e1x = d2x - d1x, e1y = d2y - d1y, e2x = -d2x, e2y = -d2y;
+    const long long adj0 = (e0y > 0 || (e0y == 0 && e0x <= 0)) ? 1 : 0;
+    const long long adj1 = (e1y > 0 || (e1y == 0 && e1x <= 0)) ? 1 : 0;
+    const long long adj2 = (e2y > 0 || (e2y == 0 && e2x <= 0)) ? 1 : 0;
+    const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - (unsigned)t);
+    for (int py = py0; py <= py1; ++py) {
+      const int sy = py * 16 - bias;
+      for (int px = px0; px <= px1; ++px) {
+        const int sx = px * 16 - bias;
+        const long long v0 = (long long)(p0x - sx) * e0y - (long long)(p0y - sy) * e0x - adj0;
+        const long long v1 = (long long)(p1x - sx) * e1y - (long long)(p1y - sy) * e1x - adj1;
+        const long long v2 = (long long)(p0x - sx) * e2y - (long long)(p0y - sy) * e2x - adj2;
+        if ((v0 | v1 | v2) < 0) continue;
+        const unsigned depth = pl[0] * (unsigned)px + pl[1] * (unsigned)py + pl[2];
+        if (depth > kDepthMax) continue;  // behind the cleared depth (FineRaster.inl:338)
+        atomicMin(&zbuf[py * W + px], ((unsigned long long)depth << 32) | low);
+      }
+    }
+  }
+  if (clip_path) atomicOr(status, kStatusClipPath);
+  __syncthreads();
+
+  // ---- phase 2: shade
+  const float xs = 2.0f / (float)W, xo = 1.0f / (float)W - 1.0f;
+  const float ys = 2.0f / (float)H, yo = 1.0f / (float)H - 1.0f;
+  const float half_d = mesh.diameter / 2.f;
+  __half* img = packed + (long long)(img0 + pose) * kPackImageElems;
+  for (int i = threadIdx.x; i < W * H; i += blockDim.x) {
+    const int py = i / W, px = i - py * W;
+    const unsigned long long key = zbuf[i];
+    const int tri = key == ~0ull ? -1 : (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
+    if (rast_id_debug) rast_id_debug[(long long)pose * W * H + i] = tri + 1;
+    float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (tri >= 0) {
+      const int i0 = mesh.faces[3 * tri], i1 = mesh.faces[3 * tri + 1], i2 = mesh.faces[3 * tri + 2];
+      const float* v0 = mesh.vertices + 3 * i0;
+      const float* v1 = mesh.vertices + 3 * i1;
+      const float* v2 = mesh.vertices + 3 * i2;
+      const ClipV p0 = clip_vertex(a, v0), p1 = clip_vertex(a, v1), p2 = clip_vertex(a, v2);
+      const float fx = xs * (float)px + xo;
+      const float fy = ys * (float)py + yo;
+      const float p0x = p0.x - fx * p0.w, p0y = p0.y - fy * p0.w;
+      const float p1x = p1.x - fx * p1.w, p1y = p1.y - fy * p1.w;
+      const float p2x = p2.x - fx * p2.w, p2y = p2.y - fy * p2.w;
+      const float a0 = p1x * p2y - p1y * p2x;
+      const float a1 = p2x * p0y - p2y * p0x;
+      const float a2 = p0x * p1y - p0y * p1x;
+      const float iw = 1.f / ((a0 + a1) + a2);
+      const float b0 = __saturatef(a0 * iw);
+      const float b1 = __saturatef(a1 * iw);
+      const float b2 = (1.f - b0) - b1;
+      // xyz in the camera frame (transform_points_kernel + interpolate)
+      float xyz[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float q0 = ((a.rot[3 * r] * v0[0] + a.rot[3 * r + 1] * v0[1]) + a.rot[3 * r + 2] * v0[2]) + a.t[r];
+        const float q1 = ((a.rot[3 * r] * v1[0] + a.rot[3 * r + 1] * v1[1]) + a.rot[3 * r + 2] * v1[2]) + a.t[r];
+        const float q2 = ((a.rot[3 * r] * v2[0] + a.rot[3 * r + 1] * v2[1]) + a.rot[3 * r + 2] * v2[2]) + a.t[r];
+        xyz[r] = (b0 * q0 + b1 * q1) + b2 * q2;
+      }
+      // texcoords
+      const float* t0 = mesh.texcoords + 2 * i0;
+      const float* t1 = mesh.texcoords + 2 * i1;
+      const float* t2 = mesh.texcoords + 2 * i2;
+      float u = (b0 * t0[0] + b1 * t1[0]) + b2 * t2[0];
+      float v = (b0 * t0[1] + b1 * t1[1]) + b2 * t2[1];
+      // diffuse (transform_normals_kernel + interpolate)
+      float dif;
+      {
+        float dv[3];
+        const int vi[3] = {i0, i1, i2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float* nrm = mesh.normals + 3 * vi[k];
+          const float nx = (a.rot[0] * nrm[0] + a.rot[1] * nrm[1]) + a.rot[2] * nrm[2];
+          const float ny = (a.rot[3] * nrm[0] + a.rot[4] * nrm[1]) + a.rot[5] * nrm[2];
+          const float nz = (a.rot[6] * nrm[0] + a.rot[7] * nrm[1]) + a.rot[8] * nrm[2];
+          const float l2 = sqrtf((nx * nx + ny * ny) + nz * nz);
+          const float val = l2 == 0.f ? 0.f : -nz / l2;
+          dv[k] = fminf(fmaxf(val, 0.f), 1.f);
+        }
+        dif = (b0 * dv[0] + b1 * dv[1]) + b2 * dv[2];
+      }
+      // bilinear texture fetch, wrap
+      const int tw = mesh.tex_w, th = mesh.tex_h;
+      u = u - floorf(u);
+      v = v - floorf(v);
+      u = u * (float)tw - 0.5f;
+      v = v * (float)th - 0.5f;
+      int iu0 = (int)floorf(u), iv0 = (int)floorf(v);
+      int iu1 = iu0 + 1, iv1 = iv0 + 1;
+      const float fu = u - (float)iu0, fv = v - (float)iv0;
+      if (iu0 < 0) iu0 += tw;
+      if (iv0 < 0) iv0 += th;
+      if (iu1 >= tw) iu1 -= tw;
+      if (iv1 >= th) iv1 -= th;
+      const float* c00 = mesh.texture + 3 * ((long long)iv0 * tw + iu0);
+      const float* c10 = mesh.texture + 3 * ((long long)iv0 * tw + iu1);
+      const float* c01 = mesh.texture + 3 * ((long long)iv1 * tw + iu0);
+      const float* c11 = mesh.texture + 3 * ((long long)iv1 * tw + iu1);
+      const float light = 0.8f + dif * 0.5f;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float top = c00[ch] + fu * (c10[ch] - c00[ch]);
+        const float bot = c01[ch] + fu * (c11[ch] - c01[ch]);
+        const float col = top + fv * (bot - top);
+        o[ch] = fminf(fmaxf(col * light, 0.f), 1.f);
+      }
+      // normalise (threshold_and_downscale_pointcloud_kernel)
+      const bool invalid = xyz[2] < kMinDepth;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float q = (xyz[r] - a.t[r]) / half_d;
+        o[3 + r] = (invalid || fabsf(q) > kMaxDepth) ? 0.f : q;
+      }
+    }
+    const int yimg = H - 1 - py;
+    uint4 pk;
+    __half2* hp = reinterpret_cast<__half2*>(&pk);
+    hp[0] = __floats2half2_rn(o[0], o[1]);
+    hp[1] = __floats2half2_rn(o[2], o[3]);
+    hp[2] = __floats2half2_rn(o[4], o[5]);
+    hp[3] = __floats2half2_rn(0.f, 0.f);
+    *reinterpret_cast<uint4*>(img + ((long long)yimg * kStemPitch + kStemPad + px) * kPackC) = pk;
+  }
+}
+
+// ------------------------------------------------------------------ observed crop
+// TransfProcess, foundationpose_render.cpp:731-812: cvcuda::WarpPerspective (rgb bilinear -> u8,
+// xyz nearest, constant-0 border) + ConvertTo(1/255) + normalise + pack.
+__global__ void warp_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ xyz, int h, int w,
+                            const PoseAux* __restrict__ aux_all, float half_d, __half* __restrict__ packed,
+                            int img0) {
+  const int pose = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kCrop * kCrop) return;
+  const PoseAux& a = aux_all[pose];
+  const int y = i / kCrop, x = i - y * kCrop;
+  const float sx = a.inv_sx * (float)x + a.left;
+  const float sy = a.inv_sy * (float)y + a.top;
+  float o[6];
+  {
+    const float fx0 = floorf(sx), fy0 = floorf(sy);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float fx = sx - fx0, fy = sy - fy0;
+    const float w00 = (1.f - fx) * (1.f - fy), w10 = fx * (1.f - fy), w01 = (1.f - fx) * fy, w11 = fx * fy;
+    float acc[3] = {0.f, 0.f, 0.f};
+    auto tap = [&](int yy, int xx, float wgt) {
+      const bool ok = xx >= 0 && xx < w && yy >= 0 && yy < h;
+      const uint8_t* p = rgb + 3 * ((long long)(ok ? yy : 0) * w + (ok ? xx : 0));
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] = acc[c] + (ok ? (float)p[c] : 0.f) * wgt;
+    };
+    tap(y0, x0, w00);
+    tap(y0, x0 + 1, w10);
+    tap(y0 + 1, x0, w01);
+    tap(y0 + 1, x0 + 1, w11);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float q = fminf(fmaxf(rintf(acc[c]), 0.f), 255.f);
+      o[c] = q * (1.0f / 255.0f);
+    }
+  }
+  {
+    const int xn = (int)floorf(sx + 0.5f), yn = (int)floorf(sy + 0.5f);
+    float p[3] = {0.f, 0.f, 0.f};
+    if (xn >= 0 && xn < w && yn >= 0 && yn < h) {
+      const float* s = xyz + 3 * ((long long)yn * w + xn);
+      p[0] = s[0]; p[1] = s[1]; p[2] = s[2];
+    }
+    const bool invalid = p[2] < kMinDepth;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float q = (p[r] - a.t[r]) / half_d;
+      o[3 + r] = (invalid || fabsf(q) > kMaxDepth) ? 0.f : q;
+    }
+  }
+  uint4 pk;
+  __half2* hp = reinterpret_cast<__half2*>(&pk);
+  hp[0] = __floats2half2_rn(o[0], o[1]);
+  hp[1] = __floats2half2_rn(o[2], o[3]);
+  hp[2] = __floats2half2_rn(o[4], o[5]);
+  hp[3] = __floats2half2_rn(0.f, 0.f);
+  __half* img = packed + (long long)(img0 + pose) * kPackImageElems;
+  *reinterpret_cast<uint4*>(img + ((long long)y * kStemPitch + kStemPad + x) * kPackC) = pk;
+}
+
+}  // namespace
+
+const char* preprocess_init() {
+  cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kCrop * kCrop * 8);
+  return e == cudaSuccess ? nullptr : "cudaFuncSetAttribute(render_kernel smem) failed";
+}
+
+void launch_depth_to_xyz(const float* depth, float* xyz, int h, int w, const Intrinsics& K, cudaStream_t s) {
+  const int n = h * w;
+  depth_to_xyz_kernel<<<(n + 255) / 256, 256, 0, s>>>(depth, xyz, h, w, K.fx, K.fy, K.cx, K.cy);
+}
+
+void launch_depth_filters(const float* depth, float* eroded, float* filtered, int h, int w, cudaStream_t s) {
+  dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+  erode_depth_kernel<<<grid, block, 0, s>>>(depth, eroded, h, w);
+  bilateral_depth_kernel<<<grid, block, 0, s>>>(eroded, filtered, h, w);
+}
+
+void launch_guess_translation(const float* filtered, const uint8_t* mask, int h, int w, const Intrinsics& K,
+                              float* center, int* status, unsigned*, cudaStream_t s) {
+  guess_translation_kernel<<<1, 1024, 0, s>>>(filtered, mask, h, w, K, center, status);
+}
+
+void launch_fill_hypotheses(const float* grid, const float* center, float* poses, int n, cudaStream_t s) {
+  fill_hypotheses_kernel<<<(n * 16 + 255) / 256, 256, 0, s>>>(grid, center, poses, n);
+}
+
+void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float diameter, float crop_ratio,
+                       PoseAux* aux, cudaStream_t s) {
+  pose_setup_kernel<<<(n + 63) / 64, 64, 0, s>>>(poses, n, K, diameter, crop_ratio, aux);
+}
+
+void launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, __half* packed, int img0,
+                   int32_t* rast_id_debug, int* status, cudaStream_t s) {
+  if (n <= 0) return;
+  render_kernel<<<n, kRenderThreads, kCrop * kCrop * 8, s>>>(mesh, aux, packed, img0, rast_id_debug, status);
+}
+
+void launch_warp(const uint8_t* rgb, const float* xyz, int h, int w, const PoseAux* aux, int n, float diameter,
+                 __half* packed, int img0, cudaStream_t s) {
+  if (n <= 0) return;
+  dim3 grid((kCrop * kCrop + 255) / 256, n);
+  warp_kernel<<<grid, 256, 0, s>>>(rgb, xyz, h, w, aux, diameter / 2.f, packed, img0);
+}
+
+}  // namespace fpb

@@ -1,0 +1,72 @@
+// RGB-D preprocessing, hypothesis sampling, fused render and crop/warp kernels (preprocess.cu).
+// Everything here is fp32 arithmetic written in the reference's operation order and compiled
+// with -fmad=false, so that integer decisions (window rounding, sub-pixel snapping, coverage,
+// depth test) are bit-identical to the CPU oracle; the packed result is stored as fp16.
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace fpb {
+
+constexpr int kCrop = 160;
+constexpr int kPackC = 8;                 // rgb(3) + xyz(3) + 2 zero channels
+constexpr int kStemPad = 4;               // zero pixels stored left of every row
+constexpr int kStemPitch = kCrop + kStemPad;  // pixels per stored row
+constexpr long long kPackImageElems = (long long)kCrop * kStemPitch * kPackC;
+
+struct Intrinsics {
+  float fx, k01, cx, fy, cy;
+  float kinv[9];   // row-major K^-1 (computed in double on the host)
+  float proj[16];  // row-major GL projection for the current image size
+  int img_h, img_w;
+};
+
+// Per-hypothesis constants derived from the pose by pose_setup().
+struct PoseAux {
+  float mvp[16];  // row-major Proj * GLcam * pose
+  float a00, a11, a30, a31;
+  float inv_sx, inv_sy, left, top;  // inverse crop transform: src = (x*inv_sx + left, y*inv_sy + top)
+  float rot[9];                     // row-major R
+  float t[3];
+  float tf[9];    // row-major crop transform (debug / tests)
+  float bbox[4];  // l, t, r, b (debug / tests)
+};
+
+struct DeviceMesh {
+  const float* vertices;   // [V,3] centred
+  const float* normals;    // [V,3]
+  const float* texcoords;  // [V,2] already (u, 1-v)
+  const int32_t* faces;    // [T,3]
+  const float* texture;    // [th,tw,3] f32 = u8 * (1/255)
+  int num_vertices, num_faces, tex_h, tex_w;
+  float diameter;
+};
+
+// status word bits written by the sampler
+constexpr int kStatusEmptyMask = 1;
+constexpr int kStatusNoDepth = 2;
+constexpr int kStatusClipPath = 4;  // some triangle needed cudaraster's clip path (dropped)
+
+void launch_depth_to_xyz(const float* depth, float* xyz, int h, int w, const Intrinsics& K,
+                         cudaStream_t s);
+void launch_depth_filters(const float* depth, float* eroded, float* filtered, int h, int w,
+                          cudaStream_t s);
+// Mask bounding box + median depth + K^-1 back-projection; writes center[3] and status.
+void launch_guess_translation(const float* filtered, const uint8_t* mask, int h, int w,
+                              const Intrinsics& K, float* center, int* status, unsigned* scratch,
+                              cudaStream_t s);
+// poses[i] = grid[i] with translation = center (col-major 4x4).
+void launch_fill_hypotheses(const float* grid, const float* center, float* poses, int n,
+                            cudaStream_t s);
+void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float diameter,
+                       float crop_ratio, PoseAux* aux, cudaStream_t s);
+// Rasterise + shade + flip + normalise + pack hypothesis i into packed image `img0 + i`.
+void launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, __half* packed, int img0,
+                   int32_t* rast_id_debug, int* status, cudaStream_t s);
+// Crop/warp the observed rgb + xyz, normalise, pack into packed image `img0 + i`.
+void launch_warp(const uint8_t* rgb, const float* xyz, int h, int w, const PoseAux* aux, int n,
+                 float diameter, __half* packed, int img0, cudaStream_t s);
+const char* preprocess_init();  // kernel attributes; nullptr on success
+
+}  // namespace fpb

@@ -1,0 +1,691 @@
+// Session object + C ABI (include/fpb200.h): the orchestration the reference does in
+// detection_6d_foundationpose/src/foundationpose.cpp (class FoundationPose), re-designed so that one
+// Register is a fixed sequence of launches on one stream with a single device->host read at the end
+// (the reference synchronises >= 12 times per call and copies every pose separately).
+#include <array>
+#include <cmath>
+#include <functional>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/fpb200.h"
+#include "common.h"
+#include "net_ops.h"
+#include "network.h"
+#include "preprocess.h"
+
+using namespace fpb;
+
+namespace {
+
+constexpr int kGridPoses = 252;  // 42 icosphere views x 6 in-plane rotations
+constexpr float kRefineCropRatio = 1.2f, kScoreCropRatio = 1.1f;  // foundationpose.cpp:84-85
+constexpr int kExchLd = 512 + 16;  // per-hypothesis exchange row: scorer feature + refined pose
+constexpr int kNumStages = 7;
+
+// ---- rotation grid: foundationpose_sampling.cpp:56-121,178-237 (host, once per session)
+struct V3 { float x, y, z; };
+V3 normalized(V3 v) {
+  const float n = std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+  return {v.x / n, v.y / n, v.z / n};
+}
+V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+std::vector<V3> icosphere(unsigned n_views) {
+  std::vector<V3> verts;
+  std::vector<std::array<int, 3>> faces;
+  const float t = (float)((1.0 + std::sqrt(5.0)) / 2.0);
+  const V3 raw[12] = {{-1, t, 0}, {1, t, 0}, {-1, -t, 0}, {1, -t, 0}, {0, -1, t}, {0, 1, t},
+                      {0, -1, -t}, {0, 1, -t}, {t, 0, -1}, {t, 0, 1}, {-t, 0, -1}, {-t, 0, 1}};
+  for (auto& v : raw) verts.push_back(normalized(v));
+  const int f0[20][3] = {{0, 11, 5}, {0, 5, 1}, {0, 1, 7}, {0, 7, 10}, {0, 10, 11}, {1, 5, 9}, {5, 11, 4},
+                         {11, 10, 2}, {10, 7, 6}, {7, 1, 8}, {3, 9, 4}, {3, 4, 2}, {3, 2, 6}, {3, 6, 8},
+                         {3, 8, 9}, {4, 9, 5}, {2, 4, 11}, {6, 2, 10}, {8, 6, 7}, {9, 8, 1}};
+  for (auto& f : f0) faces.push_back({f[0], f[1], f[2]});
+  std::map<long long, int> cache;
+  auto mid = [&](int i, int j) {
+    const long long key = ((long long)std::min(i, j) << 32) + std::max(i, j);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const V3 a = verts[i], b = verts[j];
+    verts.push_back(normalized({(a.x + b.x) / 2.f, (a.y + b.y) / 2.f, (a.z + b.z) / 2.f}));
+    return cache[key] = (int)verts.size() - 1;
+  };
+  while (verts.size() < n_views) {
+    std::vector<std::array<int, 3>> nf;
+    for (auto& f : faces) {
+      const int ab = mid(f[0], f[1]), bc = mid(f[1], f[2]), ca = mid(f[2], f[0]);
+      nf.push_back({f[0], ab, ca});
+      nf.push_back({f[1], bc, ab});
+      nf.push_back({f[2], ca, bc});
+      nf.push_back({ab, bc, ca});
+    }
+    faces.swap(nf);
+  }
+  return verts;
+}
+
+// 252 column-major 4x4 ob_in_cam matrices, icosphere-vertex major, in-plane angle minor.
+std::vector<float> make_rotation_grid() {
+  std::vector<float> out;
+  for (const V3& v : icosphere(40)) {
+    const V3 z = normalized({-v.x, -v.y, -v.z});
+    V3 x = cross({0, 0, 1}, z);
+    if (x.x == 0 && x.y == 0 && x.z == 0) x = {1, 0, 0};
+    x = normalized(x);
+    const V3 y = normalized(cross(z, x));
+    for (int step = 0; step < 6; ++step) {
+      const float a = (float)(step * 60.0 * M_PI / 180.0);
+      const float c = std::cos(a), s = std::sin(a);
+      // cam_in_ob = [x y z | v] * Rz(a)
+      const double r[3][3] = {{(double)(x.x * c + y.x * s), (double)(-x.x * s + y.x * c), z.x},
+                              {(double)(x.y * c + y.y * s), (double)(-x.y * s + y.y * c), z.y},
+                              {(double)(x.z * c + y.z * s), (double)(-x.z * s + y.z * c), z.z}};
+      const double tv[3] = {v.x, v.y, v.z};
+      // general inverse of the rigid-like matrix in double (the reference calls Matrix4f::inverse())
+      const double det = r[0][0] * (r[1][1] * r[2][2] - r[1][2] * r[2][1]) -
+                         r[0][1] * (r[1][0] * r[2][2] - r[1][2] * r[2][0]) +
+                         r[0][2] * (r[1][0] * r[2][1] - r[1][1] * r[2][0]);
+      double inv[3][3];
+      inv[0][0] = (r[1][1] * r[2][2] - r[1][2] * r[2][1]) / det;
+      inv[0][1] = (r[0][2] * r[2][1] - r[0][1] * r[2][2]) / det;
+      inv[0][2] = (r[0][1] * r[1][2] - r[0][2] * r[1][1]) / det;
+      inv[1][0] = (r[1][2] * r[2][0] - r[1][0] * r[2][2]) / det;
+      inv[1][1] = (r[0][0] * r[2][2] - r[0][2] * r[2][0]) / det;
+      inv[1][2] = (r[0][2] * r[1][0] - r[0][0] * r[1][2]) / det;
+      inv[2][0] = (r[1][0] * r[2][1] - r[1][1] * r[2][0]) / det;
+      inv[2][1] = (r[0][1] * r[2][0] - r[0][0] * r[2][1]) / det;
+      inv[2][2] = (r[0][0] * r[1][1] - r[0][1] * r[1][0]) / det;
+      float m[16];
+      for (int cc = 0; cc < 3; ++cc) {
+        for (int rr = 0; rr < 3; ++rr) m[4 * cc + rr] = (float)inv[rr][cc];
+        m[4 * cc + 3] = 0.f;
+      }
+      for (int rr = 0; rr < 3; ++rr)
+        m[12 + rr] = (float)(-(inv[rr][0] * tv[0] + inv[rr][1] * tv[1] + inv[rr][2] * tv[2]));
+      m[15] = 1.f;
+      out.insert(out.end(), m, m + 16);
+    }
+  }
+  return out;
+}
+
+// ProjectMatrixFromIntrinsics (y_down), foundationpose_render.cpp:151-186; fp32 like the reference.
+void projection_matrix(const float K[9], int h, int w, float out[16]) {
+  const float nc = 0.1f, fc = 100.0f;
+  const float depth = fc - nc;
+  const float q = -(fc + nc) / depth;
+  const float qn = -2.f * (fc * nc) / depth;
+  const float wf = (float)w, hf = (float)h;
+  const float m[16] = {2.f * K[0] / wf, -2.f * K[1] / wf, (-2.f * K[2] + wf) / wf, 0.f,
+                       0.f, 2.f * K[4] / hf, (2.f * K[5] - hf) / hf, 0.f,
+                       0.f, 0.f, q, qn,
+                       0.f, 0.f, -1.f, 0.f};
+  memcpy(out, m, sizeof(m));
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    n = count;
+    FPB_CUDA(cudaMalloc(&p, sizeof(T) * (count ? count : 1)));
+  }
+  void upload(const T* src, size_t count) {
+    alloc(count);
+    FPB_CUDA(cudaMemcpy(p, src, sizeof(T) * count, cudaMemcpyHostToDevice));
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct MeshEntry {
+  std::string name;
+  DevBuf<float> vertices, normals, texcoords, texture;
+  DevBuf<int32_t> faces;
+  DeviceMesh dm{};
+};
+
+struct HostResult {
+  float pose[16];
+  int best_index;
+  int status;
+};
+
+}  // namespace
+
+struct fpb200_session {
+  fpb200_options opt{};
+  float K[9];
+  int max_h = 0, max_w = 0;
+  Intrinsics intr{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[kNumStages + 1]{};
+  bool ev_valid[kNumStages + 1]{};
+  std::vector<std::unique_ptr<MeshEntry>> meshes;
+  MeshEntry* cur_mesh = nullptr;
+  DevBuf<uint8_t> rgb, mask;
+  DevBuf<float> depth, xyz, eroded, filtered, grid, poses, center, exch_local, exch_all, feats, tail_qkv,
+      tail_att, tail_out, scores, trans, rot, best_pose, all_poses;
+  DevBuf<int> status, best_index;
+  DevBuf<int32_t> rast_id;
+  DevBuf<PoseAux> aux;
+  HostResult* host_result = nullptr;  // pinned
+  std::unique_ptr<Arena> arena;
+  std::unique_ptr<Network> refiner, scorer;
+  int img_h = 0, img_w = 0;
+  bool uploaded = false;
+  int n_hyp = 0;             // total hypotheses of the current call
+  int lo = 0, hi = 0;        // local shard [lo, hi)
+  int shard_cap = 0;         // rows per rank in the padded exchange buffer
+  bool features_ready = false;
+  int launches = 0;
+  float crop_ratio_last = 0.f;
+
+  ~fpb200_session() {
+    if (host_result) cudaFreeHost(host_result);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  MeshEntry* find_mesh(const char* name) {
+    if (!name) return nullptr;
+    for (auto& m : meshes) if (m->name == name) return m.get();
+    return nullptr;
+  }
+  void mark(int i) {
+    FPB_CUDA(cudaEventRecord(ev[i], stream));
+    ev_valid[i] = true;
+  }
+  void set_shard(int n) {
+    n_hyp = n;
+    const int world = opt.shard_world, rank = opt.shard_rank;
+    const int base = n / world, rem = n % world;
+    lo = rank * base + std::min(rank, rem);
+    hi = lo + base + (rank < rem ? 1 : 0);
+    shard_cap = (n + world - 1) / world;
+    features_ready = false;
+  }
+};
+
+namespace {
+
+int guard(const std::function<int()>& f) {
+  try {
+    return f();
+  } catch (const std::invalid_argument& e) {
+    return fail(FPB200_ERR_INVALID, "%s", e.what());
+  } catch (const CudaError& e) {
+    return fail(FPB200_ERR_CUDA, "%s", e.what());
+  } catch (const std::exception& e) {
+    return fail(FPB200_ERR_IO, "%s", e.what());
+  }
+}
+
+void do_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w) {
+  FPB_REQUIRE(rgb && depth, "rgb/depth must not be null");
+  FPB_REQUIRE(h > 0 && w > 0 && h <= s->max_h && w <= s->max_w, "image %dx%d exceeds the session maximum %dx%d", h,
+              w, s->max_h, s->max_w);
+  if (h != s->img_h || w != s->img_w) {
+    s->img_h = h;
+    s->img_w = w;
+    s->intr.img_h = h;
+    s->intr.img_w = w;
+    projection_matrix(s->K, h, w, s->intr.proj);
+  }
+  s->mark(0);
+  FPB_CUDA(cudaMemcpyAsync(s->rgb.p, rgb, (size_t)h * w * 3, cudaMemcpyHostToDevice, s->stream));
+  FPB_CUDA(cudaMemcpyAsync(s->depth.p, depth, sizeof(float) * (size_t)h * w, cudaMemcpyHostToDevice, s->stream));
+  launch_depth_to_xyz(s->depth.p, s->xyz.p, h, w, s->intr, s->stream);
+  s->launches += 1;
+  s->uploaded = true;
+  s->mark(1);
+}
+
+void do_sample(fpb200_session* s, const uint8_t* mask, MeshEntry* mesh) {
+  FPB_REQUIRE(mask, "mask must not be null");
+  const int h = s->img_h, w = s->img_w;
+  FPB_CUDA(cudaMemcpyAsync(s->mask.p, mask, (size_t)h * w, cudaMemcpyHostToDevice, s->stream));
+  launch_depth_filters(s->depth.p, s->eroded.p, s->filtered.p, h, w, s->stream);
+  launch_guess_translation(s->filtered.p, s->mask.p, h, w, s->intr, s->center.p, s->status.p, nullptr, s->stream);
+  const int n = std::min(kGridPoses, s->opt.max_hyps);
+  launch_fill_hypotheses(s->grid.p, s->center.p, s->poses.p, n, s->stream);
+  s->launches += 4;
+  s->cur_mesh = mesh;
+  s->set_shard(n);
+  s->mark(2);
+}
+
+void do_render_and_transform(fpb200_session* s, float crop_ratio) {
+  FPB_REQUIRE(s->uploaded && s->cur_mesh && s->n_hyp > 0, "upload an image and set hypotheses first");
+  const int nl = s->hi - s->lo;
+  const MeshEntry& m = *s->cur_mesh;
+  launch_pose_setup(s->poses.p + 16 * s->lo, nl, s->intr, m.dm.diameter, crop_ratio, s->aux.p, s->stream);
+  launch_render(m.dm, s->aux.p, nl, s->arena->packed, 0, s->rast_id.p, s->status.p, s->stream);
+  launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->stream);
+  s->launches += 3;
+  s->crop_ratio_last = crop_ratio;
+}
+
+void do_refine_step(fpb200_session* s) {
+  do_render_and_transform(s, kRefineCropRatio);
+  const int nl = s->hi - s->lo;
+  s->refiner->forward(nl, s->stream);
+  const WeightFile& W = s->refiner->weights();
+  launch_refine_update(s->arena->mean_t, s->arena->mean_r, W.f32("trans.head.w", 3, 512), W.f32("trans.head.b", 3),
+                       W.f32("rot.head.w", 3, 512), W.f32("rot.head.b", 3), s->cur_mesh->dm.diameter,
+                       s->poses.p + 16 * s->lo, s->trans.p, s->rot.p, nl, s->stream);
+  s->launches += s->refiner->launches_per_forward(nl) + 1;
+}
+
+__global__ void pack_exchange_kernel(const float* __restrict__ feats, const float* __restrict__ poses,
+                                     float* __restrict__ exch, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kExchLd) return;
+  const int r = i / kExchLd, c = i - r * kExchLd;
+  exch[i] = c < 512 ? feats[r * 512 + c] : poses[r * 16 + (c - 512)];
+}
+
+// exchange rows of rank r sit at [r * cap, r * cap + count_r); compact to dense [n,512] + [n,16]
+__global__ void unpack_exchange_kernel(const float* __restrict__ exch, float* __restrict__ feats,
+                                       float* __restrict__ poses, int n, int world, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kExchLd) return;
+  const int row = i / kExchLd, c = i - row * kExchLd;
+  const int base = n / world, rem = n % world;
+  // rank owning global row `row`
+  int rank, start;
+  if (row < rem * (base + 1)) {
+    rank = row / (base + 1);
+    start = rank * (base + 1);
+  } else {
+    rank = rem + (row - rem * (base + 1)) / (base > 0 ? base : 1);
+    start = rem * (base + 1) + (rank - rem) * base;
+  }
+  const float v = exch[((long long)rank * cap + (row - start)) * kExchLd + c];
+  if (c < 512) feats[row * 512 + c] = v; else poses[row * 16 + (c - 512)] = v;
+}
+
+void do_score_features(fpb200_session* s) {
+  do_render_and_transform(s, kScoreCropRatio);
+  const int nl = s->hi - s->lo;
+  s->scorer->forward(nl, s->stream);
+  const WeightFile& W = s->scorer->weights();
+  // out_proj of the self-attention applied to the token mean (linear, so it commutes with the mean)
+  launch_small_linear(s->arena->mean_t, W.f32("att.out.w", 512, 512), W.f32("att.out.b", 512), s->feats.p, nl, 512,
+                      512, s->stream);
+  pack_exchange_kernel<<<(nl * kExchLd + 255) / 256, 256, 0, s->stream>>>(s->feats.p, s->poses.p + 16 * s->lo,
+                                                                         s->exch_local.p, nl);
+  FPB_CUDA(cudaGetLastError());
+  if (s->opt.shard_world == 1)
+    FPB_CUDA(cudaMemcpyAsync(s->exch_all.p, s->exch_local.p, sizeof(float) * (size_t)nl * kExchLd,
+                             cudaMemcpyDeviceToDevice, s->stream));
+  s->launches += s->scorer->launches_per_forward(nl) + 2;
+  s->features_ready = true;
+}
+
+void do_score_finish(fpb200_session* s) {
+  FPB_REQUIRE(s->features_ready, "score_features must run before score_finish");
+  const int n = s->n_hyp;
+  const WeightFile& W = s->scorer->weights();
+  unpack_exchange_kernel<<<(n * kExchLd + 255) / 256, 256, 0, s->stream>>>(s->exch_all.p, s->feats.p, s->all_poses.p, n,
+                                                                          s->opt.shard_world, s->shard_cap);
+  FPB_CUDA(cudaGetLastError());
+  launch_small_linear(s->feats.p, W.f32("cross.qkv.w", 1536, 512), W.f32("cross.qkv.b", 1536), s->tail_qkv.p, n, 512,
+                      1536, s->stream);
+  launch_cross_attention(s->tail_qkv.p, s->tail_att.p, n, s->stream);
+  launch_small_linear(s->tail_att.p, W.f32("cross.out.w", 512, 512), W.f32("cross.out.b", 512), s->tail_out.p, n, 512,
+                      512, s->stream);
+  launch_small_linear(s->tail_out.p, W.f32("lin.w", 1, 512), W.f32("lin.b", 1), s->scores.p, n, 512, 1, s->stream);
+  launch_argmax_pose(s->scores.p, s->all_poses.p, n, s->best_index.p, s->best_pose.p, s->stream);
+  s->launches += 6;
+}
+
+// Single device->host read of the call: winning pose, its index and the status word.
+int finish_and_read(fpb200_session* s, float out_pose[16], int* best_index) {
+  FPB_CUDA(cudaMemcpyAsync(s->host_result->pose, s->best_pose.p, sizeof(float) * 16, cudaMemcpyDeviceToHost, s->stream));
+  FPB_CUDA(cudaMemcpyAsync(&s->host_result->best_index, s->best_index.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  FPB_CUDA(cudaMemcpyAsync(&s->host_result->status, s->status.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  FPB_CUDA(cudaStreamSynchronize(s->stream));
+  const int st = s->host_result->status;
+  if (st & kStatusEmptyMask) return fail(FPB200_ERR_NO_DEPTH, "[FoundationposeSampling] Mask is all zero.");
+  if (st & kStatusNoDepth) return fail(FPB200_ERR_NO_DEPTH, "[FoundationposeSampling] No valid value in mask.");
+  if (out_pose) memcpy(out_pose, s->host_result->pose, sizeof(float) * 16);
+  if (best_index) *best_index = s->host_result->best_index;
+  return FPB200_OK;
+}
+
+void reset_call(fpb200_session* s) {
+  s->launches = 0;
+  for (auto& v : s->ev_valid) v = false;
+  FPB_CUDA(cudaMemsetAsync(s->status.p, 0, sizeof(int), s->stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+void fpb200_default_options(fpb200_options* o) {
+  if (!o) return;
+  o->device = 0;
+  o->max_hyps = kGridPoses;
+  o->shard_rank = 0;
+  o->shard_world = 1;
+  o->use_cuda_graph = 0;
+}
+
+int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], int max_h, int max_w,
+                  const char* refiner_weights, const char* scorer_weights, const fpb200_options* opts,
+                  fpb200_session** out) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(out && K && meshes && num_meshes > 0, "fpb200_create: null argument");
+    FPB_REQUIRE(refiner_weights && scorer_weights, "fpb200_create: weight paths are required");
+    FPB_REQUIRE(max_h > 0 && max_w > 0, "fpb200_create: bad maximum image size");
+    std::unique_ptr<fpb200_session> s(new fpb200_session);
+    if (opts) s->opt = *opts; else fpb200_default_options(&s->opt);
+    FPB_REQUIRE(s->opt.max_hyps >= 1, "max_hyps must be >= 1");
+    FPB_REQUIRE(s->opt.shard_world >= 1 && s->opt.shard_rank >= 0 && s->opt.shard_rank < s->opt.shard_world,
+                "bad shard rank/world");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      throw CudaError("no CUDA device available: this library has no CPU fallback");
+    FPB_CUDA(cudaSetDevice(s->opt.device));
+    cudaDeviceProp prop;
+    FPB_CUDA(cudaGetDeviceProperties(&prop, s->opt.device));
+    if (prop.major != 10) throw CudaError("fpb200 targets sm_100a (B200); found a different architecture");
+    if (const char* e = preprocess_init()) throw CudaError(e);
+    memcpy(s->K, K, sizeof(float) * 9);
+    s->max_h = max_h;
+    s->max_w = max_w;
+    s->intr.fx = K[0]; s->intr.k01 = K[1]; s->intr.cx = K[2]; s->intr.fy = K[4]; s->intr.cy = K[5];
+    {  // K^-1 in double
+      double a[9];
+      for (int i = 0; i < 9; ++i) a[i] = K[i];
+      const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) +
+                         a[2] * (a[3] * a[7] - a[4] * a[6]);
+      FPB_REQUIRE(std::fabs(det) > 1e-12, "camera matrix is singular");
+      const double inv[9] = {(a[4] * a[8] - a[5] * a[7]) / det, (a[2] * a[7] - a[1] * a[8]) / det,
+                             (a[1] * a[5] - a[2] * a[4]) / det, (a[5] * a[6] - a[3] * a[8]) / det,
+                             (a[0] * a[8] - a[2] * a[6]) / det, (a[2] * a[3] - a[0] * a[5]) / det,
+                             (a[3] * a[7] - a[4] * a[6]) / det, (a[1] * a[6] - a[0] * a[7]) / det,
+                             (a[0] * a[4] - a[1] * a[3]) / det};
+      for (int i = 0; i < 9; ++i) s->intr.kinv[i] = (float)inv[i];
+    }
+    FPB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& e : s->ev) FPB_CUDA(cudaEventCreate(&e));
+    FPB_CUDA(cudaMallocHost(&s->host_result, sizeof(HostResult)));
+
+    for (int i = 0; i < num_meshes; ++i) {
+      const fpb200_mesh& m = meshes[i];
+      FPB_REQUIRE(m.name && m.vertices && m.normals && m.texcoords && m.faces && m.texture, "mesh %d: null field", i);
+      FPB_REQUIRE(m.num_vertices > 0 && m.num_faces > 0 && m.tex_h > 0 && m.tex_w > 0 && m.diameter > 0,
+                  "mesh %d: empty geometry / texture", i);
+      FPB_REQUIRE(!s->find_mesh(m.name), "duplicate mesh name '%s'", m.name);
+      std::unique_ptr<MeshEntry> e(new MeshEntry);
+      e->name = m.name;
+      std::vector<float> v((size_t)m.num_vertices * 3), tc((size_t)m.num_vertices * 2);
+      for (int k = 0; k < m.num_vertices; ++k) {
+        for (int c = 0; c < 3; ++c) v[3 * k + c] = m.vertices[3 * k + c] - m.center[c];
+        tc[2 * k] = m.texcoords[2 * k];
+        tc[2 * k + 1] = 1 - m.texcoords[2 * k + 1];
+      }
+      std::vector<float> tex((size_t)m.tex_h * m.tex_w * 3);
+      const float sc = 1.0f / 255.0f;  // cvcuda::ConvertTo(scale = 1/255), foundationpose_render.cpp:503-506
+      for (size_t k = 0; k < tex.size(); ++k) tex[k] = (float)m.texture[k] * sc;
+      for (int k = 0; k < m.num_faces * 3; ++k)
+        FPB_REQUIRE(m.faces[k] >= 0 && m.faces[k] < m.num_vertices, "mesh %d: face index out of range", i);
+      e->vertices.upload(v.data(), v.size());
+      e->normals.upload(m.normals, (size_t)m.num_vertices * 3);
+      e->texcoords.upload(tc.data(), tc.size());
+      e->texture.upload(tex.data(), tex.size());
+      e->faces.upload(m.faces, (size_t)m.num_faces * 3);
+      e->dm = DeviceMesh{e->vertices.p, e->normals.p, e->texcoords.p, e->faces.p, e->texture.p,
+                         m.num_vertices, m.num_faces, m.tex_h, m.tex_w, m.diameter};
+      s->meshes.push_back(std::move(e));
+    }
+
+    const size_t px = (size_t)max_h * max_w;
+    const int cap = s->opt.max_hyps;
+    s->rgb.alloc(px * 3); s->mask.alloc(px); s->depth.alloc(px); s->xyz.alloc(px * 3);
+    s->eroded.alloc(px); s->filtered.alloc(px);
+    const std::vector<float> grid = make_rotation_grid();
+    s->grid.upload(grid.data(), grid.size());
+    s->poses.alloc((size_t)cap * 16); s->all_poses.alloc((size_t)cap * 16);
+    s->center.alloc(4); s->status.alloc(1); s->best_index.alloc(1); s->best_pose.alloc(16);
+    s->aux.alloc(cap); s->rast_id.alloc((size_t)cap * kCrop * kCrop);
+    s->exch_local.alloc((size_t)cap * kExchLd);
+    s->exch_all.alloc(((size_t)cap + s->opt.shard_world) * kExchLd);
+    s->feats.alloc((size_t)cap * 512); s->tail_qkv.alloc((size_t)cap * 1536); s->tail_att.alloc((size_t)cap * 512);
+    s->tail_out.alloc((size_t)cap * 512); s->scores.alloc(cap); s->trans.alloc((size_t)cap * 3);
+    s->rot.alloc((size_t)cap * 3);
+    FPB_CUDA(cudaMemset(s->status.p, 0, sizeof(int)));
+    const int local_cap = (cap + s->opt.shard_world - 1) / s->opt.shard_world;
+    s->arena.reset(new Arena(local_cap));
+    s->refiner.reset(new Network(NetKind::kRefiner, refiner_weights, s->arena.get()));
+    s->scorer.reset(new Network(NetKind::kScorer, scorer_weights, s->arena.get()));
+    // the reference validates blob names at construction (foundationpose.cpp:126-139); here: head tensors
+    s->refiner->weights().f32("trans.head.w", 3, 512);
+    s->refiner->weights().f32("rot.head.w", 3, 512);
+    s->scorer->weights().f32("lin.w", 1, 512);
+    FPB_CUDA(cudaDeviceSynchronize());
+    *out = s.release();
+    return FPB200_OK;
+  });
+}
+
+void fpb200_destroy(fpb200_session* s) {
+  if (!s) return;
+  cudaStreamSynchronize(s->stream);
+  delete s;
+}
+
+int fpb200_register(fpb200_session* s, const uint8_t* rgb, const float* depth, const uint8_t* mask, int h, int w,
+                    const char* target_name, int refine_itr, float out_pose[16]) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && out_pose, "null session / output");
+    FPB_REQUIRE(s->opt.shard_world == 1, "fpb200_register needs shard_world == 1; sharded sessions use the stage API");
+    MeshEntry* mesh = s->find_mesh(target_name);
+    FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
+    FPB_REQUIRE(refine_itr >= 0, "refine_itr must be >= 0");
+    reset_call(s);
+    do_upload(s, rgb, depth, h, w);
+    do_sample(s, mask, mesh);
+    for (int i = 0; i < refine_itr; ++i) do_refine_step(s);
+    s->mark(4);
+    do_score_features(s);
+    s->mark(5);
+    do_score_finish(s);
+    s->mark(6);
+    return finish_and_read(s, out_pose, nullptr);
+  });
+}
+
+int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w, const float hyp_pose[16],
+                 const char* target_name, int refine_itr, float out_pose[16]) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && out_pose && hyp_pose, "null session / pose");
+    MeshEntry* mesh = s->find_mesh(target_name);
+    FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
+    FPB_REQUIRE(refine_itr >= 0, "refine_itr must be >= 0");
+    reset_call(s);
+    do_upload(s, rgb, depth, h, w);
+    FPB_CUDA(cudaMemcpyAsync(s->poses.p, hyp_pose, sizeof(float) * 16, cudaMemcpyHostToDevice, s->stream));
+    s->cur_mesh = mesh;
+    s->n_hyp = 1; s->lo = 0; s->hi = 1; s->shard_cap = 1; s->features_ready = false;
+    s->mark(2);
+    for (int i = 0; i < refine_itr; ++i) do_refine_step(s);
+    s->mark(4);
+    FPB_CUDA(cudaMemcpyAsync(s->host_result->pose, s->poses.p, sizeof(float) * 16, cudaMemcpyDeviceToHost, s->stream));
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    memcpy(out_pose, s->host_result->pose, sizeof(float) * 16);
+    return FPB200_OK;
+  });
+}
+
+int fpb200_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    reset_call(s);
+    do_upload(s, rgb, depth, h, w);
+    return FPB200_OK;
+  });
+}
+
+int fpb200_sample_hypotheses(fpb200_session* s, const uint8_t* mask, const char* target_name) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    if (!s->uploaded) return fail(FPB200_ERR_STATE, "fpb200_upload must be called first");
+    MeshEntry* mesh = s->find_mesh(target_name);
+    FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
+    do_sample(s, mask, mesh);
+    int st = 0;
+    FPB_CUDA(cudaMemcpyAsync(&s->host_result->status, s->status.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    st = s->host_result->status;
+    if (st & kStatusEmptyMask) return fail(FPB200_ERR_NO_DEPTH, "[FoundationposeSampling] Mask is all zero.");
+    if (st & kStatusNoDepth) return fail(FPB200_ERR_NO_DEPTH, "[FoundationposeSampling] No valid value in mask.");
+    return FPB200_OK;
+  });
+}
+
+int fpb200_set_hypotheses(fpb200_session* s, const float* poses, int n, const char* target_name) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && poses, "null argument");
+    FPB_REQUIRE(n >= 1 && n <= s->opt.max_hyps, "hypothesis count %d outside [1,%d]", n, s->opt.max_hyps);
+    MeshEntry* mesh = s->find_mesh(target_name);
+    FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
+    FPB_CUDA(cudaMemcpyAsync(s->poses.p, poses, sizeof(float) * 16 * n, cudaMemcpyHostToDevice, s->stream));
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    s->cur_mesh = mesh;
+    s->set_shard(n);
+    return FPB200_OK;
+  });
+}
+
+int fpb200_get_hypotheses(fpb200_session* s, float* poses, int capacity, int* n) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && poses && n, "null argument");
+    FPB_REQUIRE(capacity >= s->n_hyp, "capacity %d < %d hypotheses", capacity, s->n_hyp);
+    FPB_CUDA(cudaMemcpyAsync(poses, s->poses.p, sizeof(float) * 16 * s->n_hyp, cudaMemcpyDeviceToHost, s->stream));
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    *n = s->n_hyp;
+    return FPB200_OK;
+  });
+}
+
+int fpb200_render_and_transform(fpb200_session* s, float crop_ratio) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    if (!s->uploaded || !s->cur_mesh) return fail(FPB200_ERR_STATE, "upload an image and set hypotheses first");
+    do_render_and_transform(s, crop_ratio);
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    return FPB200_OK;
+  });
+}
+
+int fpb200_refine_step(fpb200_session* s) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    if (!s->uploaded || !s->cur_mesh) return fail(FPB200_ERR_STATE, "upload an image and set hypotheses first");
+    do_refine_step(s);
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    return FPB200_OK;
+  });
+}
+
+int fpb200_score_features(fpb200_session* s) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    if (!s->uploaded || !s->cur_mesh) return fail(FPB200_ERR_STATE, "upload an image and set hypotheses first");
+    do_score_features(s);
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    return FPB200_OK;
+  });
+}
+
+int fpb200_feature_buffers(fpb200_session* s, void** local_dev, int* n_local, int* local_offset, void** all_dev,
+                           int* n_all) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    if (local_dev) *local_dev = s->exch_local.p;
+    if (n_local) *n_local = s->hi - s->lo;
+    if (local_offset) *local_offset = s->lo;
+    if (all_dev) *all_dev = s->exch_all.p;
+    if (n_all) *n_all = s->n_hyp;
+    return FPB200_OK;
+  });
+}
+
+int fpb200_score_finish(fpb200_session* s, int* best_index, float out_pose[16]) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    if (!s->features_ready) return fail(FPB200_ERR_STATE, "fpb200_score_features must be called first");
+    do_score_finish(s);
+    return finish_and_read(s, out_pose, best_index);
+  });
+}
+
+int fpb200_read_buffer(fpb200_session* s, const char* name, void* host_dst, size_t capacity, size_t* written) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && name && host_dst, "null argument");
+    const std::string nm(name);
+    const int nl = s->hi - s->lo;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    const size_t img_b = (size_t)kPackImageElems * 2;
+    if (nm == "render_input") { src = s->arena->packed; bytes = img_b * nl; }
+    else if (nm == "transf_input") { src = s->arena->packed + (size_t)nl * kPackImageElems; bytes = img_b * nl; }
+    else if (nm == "xyz_map") { src = s->xyz.p; bytes = sizeof(float) * 3 * s->img_h * s->img_w; }
+    else if (nm == "depth_filtered") { src = s->filtered.p; bytes = sizeof(float) * s->img_h * s->img_w; }
+    else if (nm == "scores") { src = s->scores.p; bytes = sizeof(float) * s->n_hyp; }
+    else if (nm == "trans") { src = s->trans.p; bytes = sizeof(float) * 3 * nl; }
+    else if (nm == "rot") { src = s->rot.p; bytes = sizeof(float) * 3 * nl; }
+    else if (nm == "features") { src = s->feats.p; bytes = sizeof(float) * 512 * s->n_hyp; }
+    else if (nm == "rast_id") { src = s->rast_id.p; bytes = sizeof(int32_t) * kCrop * kCrop * nl; }
+    else if (nm == "tokens") { src = s->arena->d0; bytes = (size_t)2 * 400 * 512 * nl; }
+    else if (nm == "center") { src = s->center.p; bytes = sizeof(float) * 3; }
+    else if (nm == "status") { src = s->status.p; bytes = sizeof(int); }
+    else if (nm == "pose_aux") { src = s->aux.p; bytes = sizeof(PoseAux) * nl; }
+    else return fail(FPB200_ERR_INVALID, "unknown buffer '%s'", name);
+    FPB_REQUIRE(capacity >= bytes, "buffer '%s' needs %zu bytes, got %zu", name, bytes, capacity);
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    FPB_CUDA(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
+    if (written) *written = bytes;
+    return FPB200_OK;
+  });
+}
+
+int fpb200_last_timings(fpb200_session* s, float* ms, int capacity) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && ms, "null argument");
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    int filled = 0;
+    int prev = -1;
+    for (int i = 0; i < kNumStages && filled < capacity; ++i) ms[filled++] = 0.f;
+    for (int i = 0; i <= kNumStages - 1; ++i) {
+      if (!s->ev_valid[i]) continue;
+      if (prev >= 0 && i - 1 < capacity) {
+        float t = 0.f;
+        FPB_CUDA(cudaEventElapsedTime(&t, s->ev[prev], s->ev[i]));
+        ms[i - 1] = t;
+      }
+      prev = i;
+    }
+    return filled;
+  });
+}
+
+int fpb200_flops_per_hypothesis(fpb200_session* s, double* refiner, double* scorer) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    if (refiner) *refiner = s->refiner->flops_per_hypothesis();
+    if (scorer) *scorer = s->scorer->flops_per_hypothesis();
+    return FPB200_OK;
+  });
+}
+
+int fpb200_last_launch_count(fpb200_session* s) { return s ? s->launches : 0; }
+
+}  // extern "C"

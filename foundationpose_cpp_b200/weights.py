@@ -1,0 +1,133 @@
+"""Weight-file exporter: PyTorch state_dict of the refine / score network -> flat FPB2W file.
+
+The flat file replaces the serialized TensorRT engine the reference loads
+(easy_deploy_tool/inference_core/trt_core/src/trt_core.cpp:185-215).  BatchNorm is folded into the
+preceding convolution, convolution weights are stored K-major in the layout csrc/conv_gemm.cu
+consumes (see layouts.py), everything the tensor cores touch is fp16, everything else fp32.
+
+File layout (little endian):
+  char[8]  "FPB2W001"
+  u32      kind (0 = refiner, 1 = scorer), u32 tensor count
+  per tensor: char[48] name, u32 dtype (0 = f16, 1 = f32), u32 ndim, u32 dims[4], u64 offset, u64 nbytes
+  payload, every tensor 256-byte aligned
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict
+
+import numpy as np
+import torch
+
+from . import layouts
+
+MAGIC = b"FPB2W001"
+KIND_REFINER, KIND_SCORER = 0, 1
+
+
+def _fold(sd: Dict[str, torch.Tensor], conv: str, bn: str, eps: float = 1e-5):
+    w, b = sd[conv + ".weight"].float(), sd[conv + ".bias"].float()
+    if bn + ".weight" in sd:
+        s = sd[bn + ".weight"].float() / torch.sqrt(sd[bn + ".running_var"].float() + eps)
+        w = w * s[:, None, None, None]
+        b = (b - sd[bn + ".running_mean"].float()) * s + sd[bn + ".bias"].float()
+    return w, b
+
+
+def _backbone_tensors(sd, p="backbone."):
+    t = {}
+    w, b = _fold(sd, p + "encodeA.0.conv", p + "encodeA.0.bn")
+    t["enc.stem.w"], t["enc.stem.b"] = layouts.pack_stem7(w).half(), b
+    w, b = _fold(sd, p + "encodeA.1.conv", p + "encodeA.1.bn")
+    t["enc.a1.w"], t["enc.a1.b"] = layouts.pack_conv3x3(w).half(), b
+    for r, idx in enumerate((2, 3)):
+        for c in (1, 2):
+            w, b = _fold(sd, f"{p}encodeA.{idx}.conv{c}", f"{p}encodeA.{idx}.bn{c}")
+            t[f"enc.a.r{r}.c{c}.w"], t[f"enc.a.r{r}.c{c}.b"] = layouts.pack_conv3x3(w).half(), b
+    for r, idx in enumerate((0, 1)):
+        for c in (1, 2):
+            w, b = _fold(sd, f"{p}encodeAB.{idx}.conv{c}", f"{p}encodeAB.{idx}.bn{c}")
+            t[f"enc.ab.r{r}.c{c}.w"], t[f"enc.ab.r{r}.c{c}.b"] = layouts.pack_conv3x3(w).half(), b
+    w, b = _fold(sd, p + "encodeAB.2.conv", p + "encodeAB.2.bn")
+    t["enc.ab.down.w"], t["enc.ab.down.b"] = layouts.pack_conv3x3(w).half(), b
+    for r, idx in enumerate((3, 4)):
+        for c in (1, 2):
+            w, b = _fold(sd, f"{p}encodeAB.{idx}.conv{c}", f"{p}encodeAB.{idx}.bn{c}")
+            t[f"enc.ab.r{r + 2}.c{c}.w"], t[f"enc.ab.r{r + 2}.c{c}.b"] = layouts.pack_conv3x3(w).half(), b
+    t["pos.table"] = sd[p + "pe"].float()[:400]
+    return t
+
+
+def refiner_tensors(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    t = _backbone_tensors(sd)
+    for h in ("trans", "rot"):
+        q = f"{h}_head.0."
+        t[f"{h}.qkv.w"], t[f"{h}.qkv.b"] = sd[q + "self_attn.in_proj_weight"].half(), sd[q + "self_attn.in_proj_bias"].float()
+        t[f"{h}.out.w"], t[f"{h}.out.b"] = sd[q + "self_attn.out_proj.weight"].half(), sd[q + "self_attn.out_proj.bias"].float()
+        t[f"{h}.ln1.g"], t[f"{h}.ln1.b"] = sd[q + "norm1.weight"].float(), sd[q + "norm1.bias"].float()
+        t[f"{h}.ff1.w"], t[f"{h}.ff1.b"] = sd[q + "linear1.weight"].half(), sd[q + "linear1.bias"].float()
+        t[f"{h}.ff2.w"], t[f"{h}.ff2.b"] = sd[q + "linear2.weight"].half(), sd[q + "linear2.bias"].float()
+        t[f"{h}.ln2.g"], t[f"{h}.ln2.b"] = sd[q + "norm2.weight"].float(), sd[q + "norm2.bias"].float()
+        t[f"{h}.head.w"], t[f"{h}.head.b"] = sd[f"{h}_head.1.weight"].float(), sd[f"{h}_head.1.bias"].float()
+    return t
+
+
+def scorer_tensors(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    t = _backbone_tensors(sd)
+    t["att.qkv.w"], t["att.qkv.b"] = sd["att.in_proj_weight"].half(), sd["att.in_proj_bias"].float()
+    t["att.out.w"], t["att.out.b"] = sd["att.out_proj.weight"].float(), sd["att.out_proj.bias"].float()
+    t["cross.qkv.w"], t["cross.qkv.b"] = sd["att_cross.in_proj_weight"].float(), sd["att_cross.in_proj_bias"].float()
+    t["cross.out.w"], t["cross.out.b"] = sd["att_cross.out_proj.weight"].float(), sd["att_cross.out_proj.bias"].float()
+    t["lin.w"], t["lin.b"] = sd["linear.weight"].float(), sd["linear.bias"].float()
+    return t
+
+
+def write_weight_file(path: str, kind: int, tensors: Dict[str, torch.Tensor]) -> None:
+    names = list(tensors)
+    header_size = 8 + 8 + len(names) * (48 + 4 + 4 + 16 + 8 + 8)
+    off = (header_size + 255) // 256 * 256
+    entries, blobs = [], []
+    for n in names:
+        a = tensors[n].detach().cpu().contiguous()
+        assert a.dtype in (torch.float16, torch.float32), (n, a.dtype)
+        assert a.dim() <= 4 and len(n) < 48
+        raw = a.numpy().tobytes()
+        dims = list(a.shape) + [1] * (4 - a.dim())
+        entries.append(struct.pack("<48sII4IQQ", n.encode(), 0 if a.dtype == torch.float16 else 1, a.dim(), *dims,
+                                   off, len(raw)))
+        blobs.append((off, raw))
+        off = (off + len(raw) + 255) // 256 * 256
+    with open(path, "wb") as f:
+        f.write(MAGIC)
+        f.write(struct.pack("<II", kind, len(names)))
+        for e in entries:
+            f.write(e)
+        for o, raw in blobs:
+            f.seek(o)
+            f.write(raw)
+        f.truncate(off)
+
+
+def export_refiner(path: str, state_dict) -> None:
+    write_weight_file(path, KIND_REFINER, refiner_tensors(state_dict))
+
+
+def export_scorer(path: str, state_dict) -> None:
+    write_weight_file(path, KIND_SCORER, scorer_tensors(state_dict))
+
+
+def read_weight_file(path: str) -> Dict[str, np.ndarray]:
+    """Reader (tests / tooling)."""
+    out = {}
+    with open(path, "rb") as f:
+        buf = f.read()
+    assert buf[:8] == MAGIC
+    _, n = struct.unpack_from("<II", buf, 8)
+    p = 16
+    for _ in range(n):
+        name, dt, nd, d0, d1, d2, d3, off, nb = struct.unpack_from("<48sII4IQQ", buf, p)
+        p += 48 + 4 + 4 + 16 + 8 + 8
+        arr = np.frombuffer(buf, dtype=np.float16 if dt == 0 else np.float32, count=nb // (2 if dt == 0 else 4),
+                            offset=off).reshape([d0, d1, d2, d3][:nd])
+        out[name.rstrip(b"\0").decode()] = arr
+    return out

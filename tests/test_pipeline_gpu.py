@@ -1,0 +1,177 @@
+"""GPU parity of the hot path through the C ABI against the CPU oracle (oracle/), same seeded inputs.
+
+Tolerances (stated per test):
+  * integer work (visibility ids, crop-window rounding) ............ bit-exact
+  * packed network inputs (fp16 storage of fp32 arithmetic) ........ equal to the oracle value rounded
+    to fp16, except <= 0.1 % of elements that may differ by one fp16 ulp (fp32 contraction in numpy vs CUDA)
+  * network outputs (fp16 tensor-core path vs fp32 PyTorch) ......... |err| <= 3e-2 * max|ref| + 3e-3
+  * refined pose ................................................... rotation <= 0.2 deg, translation <= 0.5 mm
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from foundationpose_cpp_b200 import api, synth
+from oracle import fp_oracle as O
+from oracle import nets
+import fp_helpers as helpers
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def env(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("weights"))
+    rp, sp = helpers.write_seeded_weights(d)
+    mesh = synth.uv_ellipsoid("mustard_proxy", slices=64, stacks=33, tex_size=256, seed=0)
+    rgb, depth, mask, gt = synth.make_scene(mesh)
+    model = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], synth.DEFAULT_K,
+                                          max_h=480, max_w=640)
+    yield {"model": model, "mesh": mesh, "omesh": helpers.oracle_mesh(mesh), "rgb": rgb, "depth": depth,
+           "mask": mask, "gt": gt, "K": synth.DEFAULT_K}
+    model.close()
+
+
+def test_depth_to_xyz_exact(env):
+    m = env["model"]
+    m.upload(env["rgb"], env["depth"])
+    got = m.read_buffer("xyz_map", np.float32, 480 * 640 * 3).reshape(480, 640, 3)
+    ref = O.depth_to_xyz(env["depth"], env["K"])
+    assert np.array_equal(got, ref)
+
+
+def test_sampler_matches_oracle(env):
+    m = env["model"]
+    m.upload(env["rgb"], env["depth"])
+    m.sample_hypotheses(env["mask"], "mustard_proxy")
+    got = m.get_hypotheses()
+    ref = O.sample_hypotheses(env["depth"], env["mask"], env["K"])
+    assert got.shape == (252, 4, 4)
+    np.testing.assert_allclose(got[:, :3, :3], ref[:, :3, :3], atol=2e-6)
+    np.testing.assert_allclose(got[:, :3, 3], ref[:, :3, 3], rtol=2e-6, atol=1e-7)
+    filt = m.read_buffer("depth_filtered", np.float32, 480 * 640).reshape(480, 640)
+    np.testing.assert_allclose(filt, O.bilateral_filter_depth(O.erode_depth(env["depth"])), rtol=1e-5, atol=1e-6)
+
+
+def test_sampler_failure_modes(env):
+    m = env["model"]
+    m.upload(env["rgb"], env["depth"])
+    with pytest.raises(Exception) as e:
+        m.sample_hypotheses(np.zeros_like(env["mask"]), "mustard_proxy")
+    assert "Mask is all zero" in str(e.value)
+    m.upload(env["rgb"], np.zeros_like(env["depth"]))
+    with pytest.raises(Exception) as e:
+        m.sample_hypotheses(env["mask"], "mustard_proxy")
+    assert "No valid value" in str(e.value)
+    with pytest.raises(Exception):
+        m.sample_hypotheses(env["mask"], "no_such_object")
+
+
+def _fp16_close(got, ref, what):
+    ref16 = ref.astype(np.float16).astype(np.float32)
+    diff = np.abs(got - ref16)
+    ulp = np.maximum(np.abs(ref16), 2.0 ** -14) * 2.0 ** -10
+    assert np.all(diff <= 1.001 * ulp), f"{what}: max diff {diff.max()} beyond one fp16 ulp"
+    frac = float((diff > 0).mean())
+    assert frac <= 1e-3, f"{what}: {frac:.2e} of elements differ from the fp16-rounded oracle"
+
+
+@pytest.mark.parametrize("crop_ratio", [1.2, 1.1])
+def test_render_and_transform_parity(env, crop_ratio):
+    m = env["model"]
+    m.upload(env["rgb"], env["depth"])
+    poses = O.sample_hypotheses(env["depth"], env["mask"], env["K"])[[0, 7, 50, 101, 200, 251]]
+    poses = np.concatenate([poses, env["gt"][None]], 0)
+    m.set_hypotheses(poses, "mustard_proxy")
+    m.render_and_transform(crop_ratio)
+    n = len(poses)
+    xyz_map = O.depth_to_xyz(env["depth"], env["K"])
+    ren, tra, info = O.render_and_transform(env["omesh"], poses, env["rgb"], xyz_map, env["K"], crop_ratio)
+    assert info["clip_path"] == 0
+    ids = m.read_buffer("rast_id", np.int32, n * 160 * 160).reshape(n, 160, 160)
+    assert np.array_equal(ids, info["ids"]), f"{int((ids != info['ids']).sum())} visibility ids differ"
+    assert (ids > 0).mean() > 0.1
+    _fp16_close(m.read_packed("transf_input", n), tra, "transf_input")
+    _fp16_close(m.read_packed("render_input", n), ren, "render_input")
+    status = m.read_buffer("status", np.int32, 1)[0]
+    assert status == 0
+
+
+def _net_close(got, ref, what):
+    tol = 3e-2 * np.abs(ref).max() + 3e-3
+    err = np.abs(got - ref).max()
+    assert err <= tol, f"{what}: max err {err:.4g} > tol {tol:.4g}"
+
+
+def _rot_err_deg(a, b):
+    c = (np.trace(a[:3, :3].astype(np.float64) @ b[:3, :3].astype(np.float64).T) - 1) / 2
+    return math.degrees(math.acos(min(1.0, max(-1.0, c))))
+
+
+def test_refiner_and_pose_update_parity(env):
+    m = env["model"]
+    refiner, _ = helpers.seeded_nets()
+    m.upload(env["rgb"], env["depth"])
+    poses = O.sample_hypotheses(env["depth"], env["mask"], env["K"])[:5]
+    m.set_hypotheses(poses, "mustard_proxy")
+    m.refine_step()
+    n = len(poses)
+    a = torch.from_numpy(m.read_packed("render_input", n))
+    b = torch.from_numpy(m.read_packed("transf_input", n))
+    with torch.no_grad():
+        t_ref, r_ref = refiner(nets.nhwc_to_inputs(a), nets.nhwc_to_inputs(b))
+    _net_close(m.read_buffer("trans", np.float32, n * 3).reshape(n, 3), t_ref.numpy(), "trans")
+    _net_close(m.read_buffer("rot", np.float32, n * 3).reshape(n, 3), r_ref.numpy(), "rot")
+    got = m.get_hypotheses()
+    ref = O.pose_update(poses, t_ref.numpy(), r_ref.numpy(), env["mesh"].diameter)
+    for i in range(n):
+        assert _rot_err_deg(got[i], ref[i]) <= 0.2
+        assert np.abs(got[i][:3, 3] - ref[i][:3, 3]).max() <= 5e-4
+
+
+def test_scorer_parity_and_argmax(env):
+    m = env["model"]
+    _, scorer = helpers.seeded_nets()
+    m.upload(env["rgb"], env["depth"])
+    poses = O.sample_hypotheses(env["depth"], env["mask"], env["K"])[::42]
+    m.set_hypotheses(poses, "mustard_proxy")
+    m.score_features()
+    n = len(poses)
+    a = torch.from_numpy(m.read_packed("render_input", n))
+    b = torch.from_numpy(m.read_packed("transf_input", n))
+    with torch.no_grad():
+        feats = scorer.features(nets.nhwc_to_inputs(a), nets.nhwc_to_inputs(b))
+        scores = scorer.tail(feats)
+    idx, pose = m.score_finish()
+    _net_close(m.read_buffer("features", np.float32, n * 512).reshape(n, 512), feats.numpy(), "features")
+    got_scores = m.read_buffer("scores", np.float32, n)
+    _net_close(got_scores, scores.numpy(), "scores")
+    ref_idx = O.argmax_first(scores.numpy())
+    srt = np.sort(scores.numpy())
+    assert idx == ref_idx or (srt[-1] - srt[-2]) < 2 * np.abs(got_scores - scores.numpy()).max()
+    assert idx == int(np.argmax(got_scores))
+    np.testing.assert_allclose(pose, m.get_hypotheses()[idx], atol=0)
+
+
+def test_register_and_track_end_to_end(env):
+    """Config 1 of BASELINE.json at reduced N is covered above; here the public calls themselves:
+    Register over all 252 hypotheses returns one of the refined hypotheses, Track refines a pose."""
+    m = env["model"]
+    ok, pose = m.Register(env["rgb"], env["depth"], env["mask"], "mustard_proxy", refine_itr=1)
+    assert ok, m.last_error
+    assert pose.shape == (4, 4) and np.isfinite(pose).all()
+    r = pose[:3, :3].astype(np.float64)
+    np.testing.assert_allclose(r @ r.T, np.eye(3), atol=1e-4)
+    assert abs(pose[2, 3] - 0.6) < 0.1  # translation guess + one refine step stays near the object
+    assert m.last_launch_count() > 40
+    ok2, pose2 = m.Track(env["rgb"], env["depth"], pose, "mustard_proxy", refine_itr=2)
+    assert ok2 and np.isfinite(pose2).all()
+    ok3, _ = m.Register(env["rgb"], env["depth"], np.zeros_like(env["mask"]), "mustard_proxy")
+    assert not ok3 and "Mask is all zero" in m.last_error
+    ok4, _ = m.Register(env["rgb"], env["depth"], env["mask"], "unknown_object")
+    assert not ok4
+    ok5, _ = m.Register(env["rgb"][:100], env["depth"], env["mask"], "mustard_proxy")
+    assert not ok5
