@@ -181,6 +181,10 @@ class FoundationPose:
         capi.check(self._lib.fpb200_upload(self._h, _fptr(rgb), _fptr(depth), depth.shape[0], depth.shape[1]))
 
     def sample_hypotheses(self, mask, target_name: str):
+        """mask=None reuses the mask already resident on the device."""
+        if mask is None:
+            capi.check(self._lib.fpb200_sample_hypotheses(self._h, None, target_name.encode()))
+            return
         mask = np.ascontiguousarray(mask, np.uint8)
         capi.check(self._lib.fpb200_sample_hypotheses(self._h, _fptr(mask), target_name.encode()))
 
@@ -240,6 +244,35 @@ class FoundationPose:
 
     def last_launch_count(self) -> int:
         return int(self._lib.fpb200_last_launch_count(self._h))
+
+    def launch_count_total(self) -> int:
+        self._lib.fpb200_launch_count_total.restype = C.c_longlong
+        return int(self._lib.fpb200_launch_count_total(self._h))
+
+    # ---- asynchronous use ----------------------------------------------------------------
+    def stream_ptr(self) -> int:
+        self._lib.fpb200_stream.restype = C.c_void_p
+        return int(self._lib.fpb200_stream(self._h) or 0)
+
+    def set_async(self, on: bool):
+        capi.check(self._lib.fpb200_set_async(self._h, int(bool(on))))
+
+    def score_finish_async(self):
+        capi.check(self._lib.fpb200_score_finish_async(self._h))
+
+    def wait(self):
+        idx = C.c_int(-1)
+        out = np.zeros(16, np.float32)
+        capi.check(self._lib.fpb200_wait(self._h, C.byref(idx), _fptr(out)))
+        return idx.value, out.reshape(4, 4).T.copy()
+
+    def set_gemm_profile(self, on: bool):
+        capi.check(self._lib.fpb200_set_gemm_profile(self._h, int(bool(on))))
+
+    def gemm_profile(self):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
+        capi.check(self._lib.fpb200_gemm_profile(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
 
 
 def CreateFoundationPoseModel(refiner_weights: str, scorer_weights: str, mesh_loaders, K, max_h: int = 1080,

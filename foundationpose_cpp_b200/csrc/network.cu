@@ -106,6 +106,7 @@ Arena::~Arena() {
 // ------------------------------------------------------------------ network
 struct Network::Plan {
   std::vector<std::function<void(cudaStream_t)>> steps;
+  std::vector<double> gemm_flops;  // per step; 0 for non-GEMM steps
   double flops = 0;
 };
 
@@ -116,14 +117,21 @@ Network::Network(NetKind kind, const std::string& weight_path, Arena* arena)
   flops_per_hyp_ = plan(1).flops;
 }
 
-Network::~Network() = default;
+Network::~Network() {
+  for (auto e : ev_pool_) cudaEventDestroy(e);
+}
 
 namespace {
+std::vector<double>* g_gemm_flops_sink = nullptr;  // set while a plan is being built
 void add_gemm(std::vector<std::function<void(cudaStream_t)>>& steps, double* flops, const ConvGemmDesc& d) {
   ConvGemmPlan pl;
   if (const char* e = build_conv_gemm(d, &pl)) throw std::runtime_error(e);
   *flops += pl.flops;
   steps.push_back([pl](cudaStream_t s) { FPB_CUDA(launch_conv_gemm(pl, s)); });
+  if (g_gemm_flops_sink) {
+    g_gemm_flops_sink->resize(steps.size(), 0.0);
+    (*g_gemm_flops_sink)[steps.size() - 1] = pl.flops;
+  }
 }
 }  // namespace
 
@@ -144,6 +152,7 @@ void Network::add_backbone(Plan& p, int n) {
     add_gemm(p.steps, &p.flops, d);
     // count the stem at its algorithmic size (7*7*6 MACs per output), not the padded K of 448
     p.flops -= 2.0 * n2 * 80 * 80 * 64 * (448 - 294);
+    p.gemm_flops.back() -= 2.0 * n2 * 80 * 80 * 64 * (448 - 294);
   }
   auto conv = [&](const __half* in, int imgs, int hw, int cin, bool s2, const std::string& name, int cout,
                   __half* out, const __half* res, int res_ld, bool phase_out, int out_ld, int img_mod, int half_coff,
@@ -214,6 +223,7 @@ Network::Plan& Network::plan(int n) {
   if (it != plans_.end()) return *it->second;
   if (n < 1 || n > arena_->cap) throw std::invalid_argument("network: hypothesis count exceeds the session capacity");
   std::unique_ptr<Plan> p(new Plan);
+  g_gemm_flops_sink = &p->gemm_flops;
   add_backbone(*p, n);
   Arena& A = *arena_;
   if (kind_ == NetKind::kRefiner) {
@@ -226,10 +236,11 @@ Network::Plan& Network::plan(int n) {
     p->steps.push_back([&A, n](cudaStream_t s) { launch_attention(A.qkv, A.att, n, 1536, 512, s); });
     p->flops += 2.0 * n * 4 * 2 * 400.0 * 400.0 * 128.0;
     p->steps.push_back([&A, n](cudaStream_t s) { launch_token_mean(A.att, A.mean_t, n, s); });
-    // out_proj is applied to the token mean by the session (it commutes with the mean); counted
-    // here at the size the reference graph runs it (per token), like the reference FLOP model
-    p->flops += 2.0 * rows * 512 * 512;
+    // out_proj is applied to the token mean by the session (it commutes with the mean)
+    p->flops += 2.0 * n * 512 * 512;
   }
+  g_gemm_flops_sink = nullptr;
+  p->gemm_flops.resize(p->steps.size(), 0.0);
   p->flops /= n;
   Plan& ref = *p;
   plans_[n] = std::move(p);
@@ -238,7 +249,43 @@ Network::Plan& Network::plan(int n) {
 
 void Network::forward(int n, cudaStream_t s) {
   Plan& p = plan(n);
-  for (auto& st : p.steps) st(s);
+  if (!profile_) {
+    for (auto& st : p.steps) st(s);
+    return;
+  }
+  p.gemm_flops.resize(p.steps.size(), 0.0);
+  for (size_t i = 0; i < p.steps.size(); ++i) {
+    if (p.gemm_flops[i] <= 0) {
+      p.steps[i](s);
+      continue;
+    }
+    while (ev_pool_.size() < ev_used_ + 2) {
+      cudaEvent_t e;
+      FPB_CUDA(cudaEventCreate(&e));
+      ev_pool_.push_back(e);
+    }
+    FPB_CUDA(cudaEventRecord(ev_pool_[ev_used_], s));
+    p.steps[i](s);
+    FPB_CUDA(cudaEventRecord(ev_pool_[ev_used_ + 1], s));
+    ev_used_ += 2;
+    ev_flops_.push_back(p.gemm_flops[i]);
+  }
+}
+
+void Network::collect_profile(double* ms, double* flops, long long* launches) {
+  double t = 0, f = 0;
+  for (size_t i = 0; i + 1 < ev_used_; i += 2) {
+    FPB_CUDA(cudaEventSynchronize(ev_pool_[i + 1]));
+    float e = 0.f;
+    FPB_CUDA(cudaEventElapsedTime(&e, ev_pool_[i], ev_pool_[i + 1]));
+    t += e;
+    f += ev_flops_[i / 2];
+  }
+  if (ms) *ms = t;
+  if (flops) *flops = f;
+  if (launches) *launches = (long long)(ev_used_ / 2);
+  ev_used_ = 0;
+  ev_flops_.clear();
 }
 
 int Network::launches_per_forward(int n) { return (int)plan(n).steps.size(); }

@@ -65,6 +65,11 @@ class Network {
   // self-attention output (before out_proj) in arena->mean_t.
   void forward(int n, cudaStream_t s);
   double flops_per_hypothesis() const { return flops_per_hyp_; }
+  // Profiling of the tcgen05 GEMM launches: when enabled every conv_gemm launch is bracketed by
+  // CUDA events on the launching stream; collect_profile() sums their durations and FLOPs since
+  // the last collect (it synchronises).
+  void set_profile(bool on) { profile_ = on; }
+  void collect_profile(double* ms, double* flops, long long* launches);
   int launches_per_forward(int n);
   const WeightFile& weights() const { return *w_; }
 
@@ -78,6 +83,10 @@ class Network {
   Arena* arena_;
   std::map<int, std::unique_ptr<Plan>> plans_;
   double flops_per_hyp_ = 0;
+  bool profile_ = false;
+  std::vector<cudaEvent_t> ev_pool_;
+  size_t ev_used_ = 0;
+  std::vector<double> ev_flops_;
 };
 
 }  // namespace fpb

@@ -182,8 +182,12 @@ struct fpb200_session {
   int lo = 0, hi = 0;        // local shard [lo, hi)
   int shard_cap = 0;         // rows per rank in the padded exchange buffer
   bool features_ready = false;
-  int launches = 0;
+  int launches = 0;        // since the last Register/Track/upload
+  long long launches_total = 0;
   float crop_ratio_last = 0.f;
+  bool async_stages = false;  // stage calls return without synchronising the stream
+  bool mask_resident = false;
+  bool profile_gemm = false;
 
   ~fpb200_session() {
     if (host_result) cudaFreeHost(host_result);
@@ -194,6 +198,13 @@ struct fpb200_session {
     if (!name) return nullptr;
     for (auto& m : meshes) if (m->name == name) return m.get();
     return nullptr;
+  }
+  void count_launches(int n) {
+    launches += n;
+    launches_total += n;
+  }
+  void stage_sync() {
+    if (!async_stages) FPB_CUDA(cudaStreamSynchronize(stream));
   }
   void mark(int i) {
     FPB_CUDA(cudaEventRecord(ev[i], stream));
@@ -239,20 +250,23 @@ void do_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h,
   FPB_CUDA(cudaMemcpyAsync(s->rgb.p, rgb, (size_t)h * w * 3, cudaMemcpyHostToDevice, s->stream));
   FPB_CUDA(cudaMemcpyAsync(s->depth.p, depth, sizeof(float) * (size_t)h * w, cudaMemcpyHostToDevice, s->stream));
   launch_depth_to_xyz(s->depth.p, s->xyz.p, h, w, s->intr, s->stream);
-  s->launches += 1;
+  s->count_launches(1);
   s->uploaded = true;
   s->mark(1);
 }
 
 void do_sample(fpb200_session* s, const uint8_t* mask, MeshEntry* mesh) {
-  FPB_REQUIRE(mask, "mask must not be null");
   const int h = s->img_h, w = s->img_w;
-  FPB_CUDA(cudaMemcpyAsync(s->mask.p, mask, (size_t)h * w, cudaMemcpyHostToDevice, s->stream));
+  if (mask) {
+    FPB_CUDA(cudaMemcpyAsync(s->mask.p, mask, (size_t)h * w, cudaMemcpyHostToDevice, s->stream));
+    s->mask_resident = true;
+  }
+  FPB_REQUIRE(s->mask_resident, "mask must not be null (no mask is resident on the device yet)");
   launch_depth_filters(s->depth.p, s->eroded.p, s->filtered.p, h, w, s->stream);
   launch_guess_translation(s->filtered.p, s->mask.p, h, w, s->intr, s->center.p, s->status.p, nullptr, s->stream);
   const int n = std::min(kGridPoses, s->opt.max_hyps);
   launch_fill_hypotheses(s->grid.p, s->center.p, s->poses.p, n, s->stream);
-  s->launches += 4;
+  s->count_launches(4);
   s->cur_mesh = mesh;
   s->set_shard(n);
   s->mark(2);
@@ -265,7 +279,7 @@ void do_render_and_transform(fpb200_session* s, float crop_ratio) {
   launch_pose_setup(s->poses.p + 16 * s->lo, nl, s->intr, m.dm.diameter, crop_ratio, s->aux.p, s->stream);
   launch_render(m.dm, s->aux.p, nl, s->arena->packed, 0, s->rast_id.p, s->status.p, s->stream);
   launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->stream);
-  s->launches += 3;
+  s->count_launches(3);
   s->crop_ratio_last = crop_ratio;
 }
 
@@ -277,7 +291,7 @@ void do_refine_step(fpb200_session* s) {
   launch_refine_update(s->arena->mean_t, s->arena->mean_r, W.f32("trans.head.w", 3, 512), W.f32("trans.head.b", 3),
                        W.f32("rot.head.w", 3, 512), W.f32("rot.head.b", 3), s->cur_mesh->dm.diameter,
                        s->poses.p + 16 * s->lo, s->trans.p, s->rot.p, nl, s->stream);
-  s->launches += s->refiner->launches_per_forward(nl) + 1;
+  s->count_launches(s->refiner->launches_per_forward(nl) + 1);
 }
 
 __global__ void pack_exchange_kernel(const float* __restrict__ feats, const float* __restrict__ poses,
@@ -322,7 +336,7 @@ void do_score_features(fpb200_session* s) {
   if (s->opt.shard_world == 1)
     FPB_CUDA(cudaMemcpyAsync(s->exch_all.p, s->exch_local.p, sizeof(float) * (size_t)nl * kExchLd,
                              cudaMemcpyDeviceToDevice, s->stream));
-  s->launches += s->scorer->launches_per_forward(nl) + 2;
+  s->count_launches(s->scorer->launches_per_forward(nl) + 2);
   s->features_ready = true;
 }
 
@@ -340,14 +354,17 @@ void do_score_finish(fpb200_session* s) {
                       512, s->stream);
   launch_small_linear(s->tail_out.p, W.f32("lin.w", 1, 512), W.f32("lin.b", 1), s->scores.p, n, 512, 1, s->stream);
   launch_argmax_pose(s->scores.p, s->all_poses.p, n, s->best_index.p, s->best_pose.p, s->stream);
-  s->launches += 6;
+  s->count_launches(6);
 }
 
 // Single device->host read of the call: winning pose, its index and the status word.
-int finish_and_read(fpb200_session* s, float out_pose[16], int* best_index) {
+void enqueue_result_read(fpb200_session* s) {
   FPB_CUDA(cudaMemcpyAsync(s->host_result->pose, s->best_pose.p, sizeof(float) * 16, cudaMemcpyDeviceToHost, s->stream));
   FPB_CUDA(cudaMemcpyAsync(&s->host_result->best_index, s->best_index.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   FPB_CUDA(cudaMemcpyAsync(&s->host_result->status, s->status.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+}
+
+int wait_result(fpb200_session* s, float out_pose[16], int* best_index) {
   FPB_CUDA(cudaStreamSynchronize(s->stream));
   const int st = s->host_result->status;
   if (st & kStatusEmptyMask) return fail(FPB200_ERR_NO_DEPTH, "[FoundationposeSampling] Mask is all zero.");
@@ -355,6 +372,11 @@ int finish_and_read(fpb200_session* s, float out_pose[16], int* best_index) {
   if (out_pose) memcpy(out_pose, s->host_result->pose, sizeof(float) * 16);
   if (best_index) *best_index = s->host_result->best_index;
   return FPB200_OK;
+}
+
+int finish_and_read(fpb200_session* s, float out_pose[16], int* best_index) {
+  enqueue_result_read(s);
+  return wait_result(s, out_pose, best_index);
 }
 
 void reset_call(fpb200_session* s) {
@@ -540,10 +562,10 @@ int fpb200_sample_hypotheses(fpb200_session* s, const uint8_t* mask, const char*
     MeshEntry* mesh = s->find_mesh(target_name);
     FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
     do_sample(s, mask, mesh);
-    int st = 0;
+    if (s->async_stages) return FPB200_OK;  // status is checked by fpb200_wait
     FPB_CUDA(cudaMemcpyAsync(&s->host_result->status, s->status.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     FPB_CUDA(cudaStreamSynchronize(s->stream));
-    st = s->host_result->status;
+    const int st = s->host_result->status;
     if (st & kStatusEmptyMask) return fail(FPB200_ERR_NO_DEPTH, "[FoundationposeSampling] Mask is all zero.");
     if (st & kStatusNoDepth) return fail(FPB200_ERR_NO_DEPTH, "[FoundationposeSampling] No valid value in mask.");
     return FPB200_OK;
@@ -580,7 +602,7 @@ int fpb200_render_and_transform(fpb200_session* s, float crop_ratio) {
     FPB_REQUIRE(s, "null session");
     if (!s->uploaded || !s->cur_mesh) return fail(FPB200_ERR_STATE, "upload an image and set hypotheses first");
     do_render_and_transform(s, crop_ratio);
-    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    s->stage_sync();
     return FPB200_OK;
   });
 }
@@ -590,7 +612,7 @@ int fpb200_refine_step(fpb200_session* s) {
     FPB_REQUIRE(s, "null session");
     if (!s->uploaded || !s->cur_mesh) return fail(FPB200_ERR_STATE, "upload an image and set hypotheses first");
     do_refine_step(s);
-    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    s->stage_sync();
     return FPB200_OK;
   });
 }
@@ -600,7 +622,7 @@ int fpb200_score_features(fpb200_session* s) {
     FPB_REQUIRE(s, "null session");
     if (!s->uploaded || !s->cur_mesh) return fail(FPB200_ERR_STATE, "upload an image and set hypotheses first");
     do_score_features(s);
-    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    s->stage_sync();
     return FPB200_OK;
   });
 }
@@ -687,5 +709,56 @@ int fpb200_flops_per_hypothesis(fpb200_session* s, double* refiner, double* scor
 }
 
 int fpb200_last_launch_count(fpb200_session* s) { return s ? s->launches : 0; }
+long long fpb200_launch_count_total(fpb200_session* s) { return s ? s->launches_total : 0; }
+void* fpb200_stream(fpb200_session* s) { return s ? (void*)s->stream : nullptr; }
+
+int fpb200_set_async(fpb200_session* s, int on) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    if (!on) FPB_CUDA(cudaStreamSynchronize(s->stream));
+    s->async_stages = on != 0;
+    return FPB200_OK;
+  });
+}
+
+int fpb200_score_finish_async(fpb200_session* s) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    if (!s->features_ready) return fail(FPB200_ERR_STATE, "fpb200_score_features must be called first");
+    do_score_finish(s);
+    enqueue_result_read(s);
+    return FPB200_OK;
+  });
+}
+
+int fpb200_wait(fpb200_session* s, int* best_index, float out_pose[16]) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    return wait_result(s, out_pose, best_index);
+  });
+}
+
+int fpb200_set_gemm_profile(fpb200_session* s, int on) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    s->refiner->set_profile(on != 0);
+    s->scorer->set_profile(on != 0);
+    return FPB200_OK;
+  });
+}
+
+int fpb200_gemm_profile(fpb200_session* s, double* ms, double* flops, long long* launches) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    double m1 = 0, f1 = 0, m2 = 0, f2 = 0;
+    long long l1 = 0, l2 = 0;
+    s->refiner->collect_profile(&m1, &f1, &l1);
+    s->scorer->collect_profile(&m2, &f2, &l2);
+    if (ms) *ms = m1 + m2;
+    if (flops) *flops = f1 + f2;
+    if (launches) *launches = l1 + l2;
+    return FPB200_OK;
+  });
+}
 
 }  // extern "C"

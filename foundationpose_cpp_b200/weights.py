@@ -131,3 +131,88 @@ def read_weight_file(path: str) -> Dict[str, np.ndarray]:
                             offset=off).reshape([d0, d1, d2, d3][:nd])
         out[name.rstrip(b"\0").decode()] = arr
     return out
+
+
+# ----------------------------------------------------------------------------- seeded weights
+def positional_table(max_len: int = 400, d: int = 512) -> torch.Tensor:
+    """PositionalEmbedding of the upstream networks: pe[p,2i] = sin(p * e^(-2i ln(1e4)/d)), pe[p,2i+1] = cos."""
+    import math
+    pe = torch.zeros(max_len, d)
+    pos = torch.arange(0, max_len, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * (-math.log(10000.0) / d))
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+def seeded_state_dict(kind: int, seed: int) -> Dict[str, torch.Tensor]:
+    """Random-init state_dict with the upstream parameter names and shapes (no checkpoint is
+    reachable offline): He-normal convolutions, non-trivial BatchNorm statistics, small transformer
+    projections.  Used by bench.py; the tests export the oracle modules' own state_dict instead."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cout, cin, k):
+        sd[name + ".weight"] = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))
+        sd[name + ".bias"] = torch.randn(cout, generator=g) * 0.05
+
+    def bn(name, c):
+        sd[name + ".weight"] = 0.6 + 0.3 * torch.rand(c, generator=g)
+        sd[name + ".bias"] = torch.randn(c, generator=g) * 0.1
+        sd[name + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+        sd[name + ".running_var"] = 0.8 + 0.4 * torch.rand(c, generator=g)
+
+    def linear(name, o, i, gain=1.0):
+        sd[name + ".weight"] = torch.randn(o, i, generator=g) * (gain / math.sqrt(i))
+        sd[name + ".bias"] = torch.randn(o, generator=g) * 0.02
+
+    def cbr(name, cout, cin, k):
+        conv(name + ".conv", cout, cin, k)
+        bn(name + ".bn", cout)
+
+    def res(name, c):
+        for i in (1, 2):
+            conv(f"{name}.conv{i}", c, c, 3)
+            bn(f"{name}.bn{i}", c)
+
+    def mha(name):
+        sd[name + ".in_proj_weight"] = torch.randn(1536, 512, generator=g) * 0.04
+        sd[name + ".in_proj_bias"] = torch.randn(1536, generator=g) * 0.02
+        linear(name + ".out_proj", 512, 512)
+
+    b = "backbone."
+    cbr(b + "encodeA.0", 64, 6, 7)
+    cbr(b + "encodeA.1", 128, 64, 3)
+    res(b + "encodeA.2", 128)
+    res(b + "encodeA.3", 128)
+    res(b + "encodeAB.0", 256)
+    res(b + "encodeAB.1", 256)
+    cbr(b + "encodeAB.2", 512, 256, 3)
+    res(b + "encodeAB.3", 512)
+    res(b + "encodeAB.4", 512)
+    sd[b + "pe"] = positional_table()
+    if kind == KIND_REFINER:
+        for h in ("trans_head", "rot_head"):
+            mha(f"{h}.0.self_attn")
+            linear(f"{h}.0.linear1", 512, 512)
+            linear(f"{h}.0.linear2", 512, 512)
+            for nrm in ("norm1", "norm2"):
+                sd[f"{h}.0.{nrm}.weight"] = 1.0 + 0.1 * torch.randn(512, generator=g)
+                sd[f"{h}.0.{nrm}.bias"] = 0.05 * torch.randn(512, generator=g)
+            linear(f"{h}.1", 3, 512, gain=0.3)
+    else:
+        mha("att")
+        mha("att_cross")
+        linear("linear", 1, 512, gain=4.0)
+    return sd
+
+
+def write_seeded(dirpath: str, refiner_seed: int = 2, scorer_seed: int = 3):
+    """Writes refiner.fpb2w / scorer.fpb2w with seeded weights into dirpath; returns the two paths."""
+    import os
+    os.makedirs(dirpath, exist_ok=True)
+    rp, sp = os.path.join(dirpath, "refiner.fpb2w"), os.path.join(dirpath, "scorer.fpb2w")
+    export_refiner(rp, seeded_state_dict(KIND_REFINER, refiner_seed))
+    export_scorer(sp, seeded_state_dict(KIND_SCORER, scorer_seed))
+    return rp, sp

@@ -82,7 +82,8 @@ int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int 
 /* UploadDataToDevice + depth->xyz (fp/src/foundationpose.cpp:267-315, fp/src/foundationpose_utils.cu:3-75). */
 int fpb200_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w);
 /* FoundationPoseSampler::GetHypPoses (fp/src/foundationpose_sampling.cpp:344-394): fills the
- * session's hypothesis set with the 252-pose grid at the guessed translation. */
+ * session's hypothesis set with the 252-pose grid at the guessed translation.  mask == NULL reuses
+ * the mask already resident on the device. */
 int fpb200_sample_hypotheses(fpb200_session* s, const uint8_t* mask, const char* target_name);
 /* Replace the session's hypothesis set (n col-major 4x4).  Track does this with n = 1. */
 int fpb200_set_hypotheses(fpb200_session* s, const float* poses, int n, const char* target_name);
@@ -111,13 +112,28 @@ int fpb200_score_finish(fpb200_session* s, int* best_index, float out_pose[16]);
 int fpb200_read_buffer(fpb200_session* s, const char* name, void* host_dst, size_t capacity_bytes,
                        size_t* bytes_written);
 /* Device-side duration of the stages of the last Register/Track (CUDA events), in ms:
- * [0] upload+xyz [1] sampler [2] refine preprocess [3] refiner net [4] score preprocess
- * [5] scorer net [6] tail; returns the number filled. */
+ * [0] upload+xyz [1] sampler [2] unused [3] refine iterations (render, warp, net, pose update)
+ * [4] score preprocess + scorer net [5] scorer tail + argmax [6] unused; returns the number filled. */
 int fpb200_last_timings(fpb200_session* s, float* ms, int capacity);
 /* Algorithmic FLOPs of one refiner / scorer forward per hypothesis, from the loaded layer list. */
 int fpb200_flops_per_hypothesis(fpb200_session* s, double* refiner, double* scorer);
-/* Number of kernel launches issued by the last Register/Track call. */
+/* Number of kernel launches issued by the last Register/Track call / since session creation. */
 int fpb200_last_launch_count(fpb200_session* s);
+long long fpb200_launch_count_total(fpb200_session* s);
+
+/* ---- asynchronous use (benchmarks, multi-GPU pipelines) ---- */
+/* The CUDA stream (cudaStream_t) every kernel of the session is launched on. */
+void* fpb200_stream(fpb200_session* s);
+/* on != 0: stage-level calls enqueue their work and return without synchronising; errors that are
+ * only known on the device (empty mask, no depth) are then reported by fpb200_wait. */
+int fpb200_set_async(fpb200_session* s, int on);
+/* fpb200_score_finish without the final synchronisation; pair with fpb200_wait. */
+int fpb200_score_finish_async(fpb200_session* s);
+int fpb200_wait(fpb200_session* s, int* best_index, float out_pose[16]);
+/* Bracket every tcgen05 GEMM launch with CUDA events on the session stream; fpb200_gemm_profile
+ * returns (and clears) the summed duration, algorithmic FLOPs and launch count since the last call. */
+int fpb200_set_gemm_profile(fpb200_session* s, int on);
+int fpb200_gemm_profile(fpb200_session* s, double* ms, double* flops, long long* launches);
 
 /* ---- kernel-level debug entry points (DEVICE pointers) ---- */
 enum {

@@ -1,0 +1,140 @@
+"""CPU tests: C-ABI surface, weight-file round trip, layouts, sharding arithmetic (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from foundationpose_cpp_b200 import build, capi
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "fpb200.h")).read()
+    names = sorted(set(re.findall(r"\b(fpb200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    lib = capi.lib()
+    for n in names:
+        assert hasattr(lib, n), f"libfpb200.so does not export {n}"
+    # no compute without a GPU: option defaults only
+    o = capi.Options()
+    lib.fpb200_default_options(ctypes.byref(o))
+    assert (o.max_hyps, o.shard_world, o.shard_rank) == (252, 1, 0)
+
+
+def test_create_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from foundationpose_cpp_b200 import api, synth, weights
+    with tempfile.TemporaryDirectory() as d:
+        rp, sp = weights.write_seeded(d)
+        mesh = synth.uv_ellipsoid("m", slices=8, stacks=5, tex_size=16)
+        with pytest.raises(Exception) as e:
+            api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], synth.DEFAULT_K, 480, 640)
+        assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_weight_file_roundtrip_and_bn_fold():
+    from foundationpose_cpp_b200 import layouts, weights
+    sd = weights.seeded_state_dict(weights.KIND_REFINER, 7)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "r.fpb2w")
+        weights.export_refiner(p, sd)
+        t = weights.read_weight_file(p)
+    assert t["enc.stem.w"].shape == (64, 448) and t["enc.stem.w"].dtype == np.float16
+    assert t["enc.ab.r3.c2.w"].shape == (512, 4608)
+    assert t["trans.qkv.w"].shape == (1536, 512) and t["rot.head.w"].shape == (3, 512)
+    assert t["pos.table"].shape == (400, 512)
+    # folded conv == conv + BN(eval) on random input
+    x = torch.randn(2, 64, 12, 12)
+    w, b = sd["backbone.encodeA.1.conv.weight"], sd["backbone.encodeA.1.conv.bias"]
+    y = F.conv2d(x, w, b, stride=2, padding=1)
+    y = F.batch_norm(y, sd["backbone.encodeA.1.bn.running_mean"], sd["backbone.encodeA.1.bn.running_var"],
+                     sd["backbone.encodeA.1.bn.weight"], sd["backbone.encodeA.1.bn.bias"], False, 0.0, 1e-5)
+    wf = torch.from_numpy(t["enc.a1.w"].astype(np.float32)).reshape(128, 3, 3, 64).permute(0, 3, 1, 2)
+    y2 = F.conv2d(x, wf, torch.from_numpy(t["enc.a1.b"]), stride=2, padding=1)
+    assert torch.allclose(y, y2, atol=2e-2, rtol=2e-2)  # fp16 weight rounding
+
+
+def test_stem_layout_is_a_valid_gemm_view():
+    """The overlapping-stride K view of the padded NHWC8 input times pack_stem7 weights == conv2d 7x7/s2."""
+    from foundationpose_cpp_b200 import layouts
+    torch.manual_seed(0)
+    x = torch.randn(1, 160, 160, 6)
+    w = torch.randn(4, 6, 7, 7)
+    buf = layouts.pad_stem_input(x).float().numpy()
+    wp = layouts.pack_stem7(w).numpy()  # [4, 7*64]
+    pitch = layouts.STEM_PITCH * 8
+    ref = F.conv2d(x.half().float().permute(0, 3, 1, 2), w, stride=2, padding=3)[0].permute(1, 2, 0).numpy()
+    for (oy, ox) in [(0, 0), (0, 79), (79, 0), (79, 79), (40, 13)]:
+        acc = np.zeros(4, np.float64)
+        for ky in range(7):
+            iy = 2 * oy + ky - 3
+            if iy < 0 or iy >= 160:
+                continue  # TMA out-of-bounds rows are zero-filled
+            start = iy * pitch + ox * 16  # 32-byte stride per output x
+            kvec = buf[start:start + 64]
+            acc += wp[:, ky * 64:(ky + 1) * 64].astype(np.float64) @ kvec
+        np.testing.assert_allclose(acc, ref[oy, ox], rtol=1e-3, atol=1e-3)
+
+
+def test_phase_split_roundtrip():
+    from foundationpose_cpp_b200 import layouts
+    x = torch.arange(2 * 8 * 8 * 3, dtype=torch.float32).reshape(2, 8, 8, 3)
+    s = layouts.phase_split(x)
+    assert s.shape == (2, 4, 4, 4, 3)
+    assert torch.equal(layouts.phase_merge(s), x)
+    assert s[0, 3, 1, 2, 0] == x[0, 3, 5, 0]  # plane 3 = odd row, odd col
+
+
+def test_shard_ranges():
+    from foundationpose_cpp_b200 import sharding
+    sizes = [sharding.shard_range(252, r, 8) for r in range(8)]
+    assert [b - a for a, b in sizes] == [32, 32, 32, 32, 31, 31, 31, 31]
+    assert sizes[0][0] == 0 and sizes[-1][1] == 252
+    for w in (1, 2, 3, 4, 8):
+        rows = [sharding.padded_row(252, w, i) for i in range(252)]
+        cap = sharding.shard_capacity(252, w)
+        for r in range(w):
+            lo, hi = sharding.shard_range(252, r, w)
+            assert rows[lo:hi] == list(range(r * cap, r * cap + hi - lo))
+    assert sharding.shard_range(1, 0, 1) == (0, 1)
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from foundationpose_cpp_b200 import sharding
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+n = 13
+cap = sharding.shard_capacity(n, world)
+lo, hi = sharding.shard_range(n, rank, world)
+local = torch.full((cap, sharding.EXCH_LD), -1.0)
+local[: hi - lo] = torch.arange(lo, hi, dtype=torch.float32)[:, None]
+allbuf = torch.empty(world * cap, sharding.EXCH_LD)
+dist.all_gather_into_tensor(allbuf, local)
+dense = torch.stack([allbuf[sharding.padded_row(n, world, i)] for i in range(n)])
+assert torch.equal(dense[:, 0], torch.arange(n, dtype=torch.float32)), dense[:, 0]
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_allgather_layout_gloo_world2():
+    with tempfile.TemporaryDirectory() as d:
+        script = os.path.join(d, "w.py")
+        open(script, "w").write(_GLOO_WORKER)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29611", script, ROOT],
+                           capture_output=True, text=True, timeout=240)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("ok") == 2
