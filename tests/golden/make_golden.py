@@ -1,0 +1,89 @@
+"""Generates tests/golden/ref_kernels_golden.npz by running the REFERENCE's own CUDA kernels
+(oracle/_ref/libref_kernels.so, built from /root/reference by oracle/Makefile) on seeded inputs.
+Run on a GPU box:   python tests/golden/make_golden.py gpurun_out/ref_kernels_golden.npz
+The inputs are stored next to the outputs so the CPU oracle can be checked without a GPU."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import fp_helpers as helpers  # noqa: E402
+from foundationpose_cpp_b200 import synth  # noqa: E402
+from oracle import fp_oracle as O  # noqa: E402
+
+
+def ref_lib():
+    return C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_kernels.so"))
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def golden_inputs():
+    mesh = synth.uv_ellipsoid("g", slices=24, stacks=13, tex_size=64, seed=5)
+    rgb, depth, mask, gt = synth.make_scene(mesh)
+    om = helpers.oracle_mesh(mesh)
+    K = synth.DEFAULT_K
+    poses = np.concatenate([gt[None], O.sample_hypotheses(depth, mask, K)[[0, 77, 190]]], 0)
+    tfs, _ = O.crop_window_tf(poses, K, 1.2, om["diameter"])
+    bbox = O.bbox2d_from_tf(tfs)
+    clip = np.stack([O.clip_vertices(om["vertices"], poses[i], bbox[i], K, 480, 640) for i in range(len(poses))])
+    pts = np.stack([O.transform_points(om["vertices"], poses[i]) for i in range(len(poses))])
+    patch = depth[180:308, 260:388].copy()  # 128x128 window around the object incl. noise and dropouts
+    return {"clip": clip.astype(np.float32), "faces": om["faces"], "pts_cam": pts.astype(np.float32),
+            "texcoords": om["texcoords"], "texture": om["texture"], "depth_patch": patch,
+            "K": np.asarray(K, np.float32)}
+
+
+def main(out_path):
+    lib = ref_lib()
+    g = golden_inputs()
+    n, v, _ = g["clip"].shape
+    t = g["faces"].shape[0]
+    H = W = 160
+    clip_d, tri_d = dev(g["clip"]), dev(g["faces"])
+    rast_d = torch.zeros(n, H, W, 4, device="cuda")
+    assert lib.ref_rasterize(ptr(clip_d), ptr(tri_d), ptr(rast_d), v, t, H, W, n) == 0
+    xyz_d = torch.zeros(n, H, W, 3, device="cuda")
+    assert lib.ref_interpolate(ptr(dev(g["pts_cam"])), ptr(rast_d), ptr(tri_d), ptr(xyz_d), v, t, 3, 3, H, W, n) == 0
+    uv_d = torch.zeros(n, H, W, 2, device="cuda")
+    assert lib.ref_interpolate(ptr(dev(g["texcoords"])), ptr(rast_d), ptr(tri_d), ptr(uv_d), v, t, 2, 2, H, W, n) == 0
+    col_d = torch.zeros(n, H, W, 3, device="cuda")
+    th, tw, _ = g["texture"].shape
+    assert lib.ref_texture(ptr(dev(g["texture"])), ptr(uv_d), ptr(col_d), th, tw, H, W, n) == 0
+    dp = dev(g["depth_patch"])
+    er, fl = torch.zeros_like(dp), torch.zeros_like(dp)
+    assert lib.ref_depth_filters(ptr(dp), ptr(er), ptr(fl), dp.shape[0], dp.shape[1]) == 0
+    xyzm = torch.zeros(*dp.shape, 3, device="cuda")
+    K = g["K"]
+    lib.ref_depth_to_xyz.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, C.c_float]
+    assert lib.ref_depth_to_xyz(ptr(dp), ptr(xyzm), dp.shape[0], dp.shape[1], float(K[0, 0]), float(K[1, 1]),
+                                float(K[0, 2]), float(K[1, 2]), 0.001) == 0
+    scores = np.array([0.1, 0.9, -0.3, 0.9, 0.5], np.float32)
+    best = lib.ref_argmax(ptr(dev(scores)), len(scores))
+    rast = rast_d.cpu().numpy()
+    sub = (slice(None), slice(0, H, 4), slice(0, W, 4))
+    np.savez_compressed(
+        out_path, **g,
+        ref_ids=rast[..., 3].astype(np.int16), ref_bary_sub=rast[sub][..., :3].astype(np.float32),
+        ref_xyz_sub=xyz_d.cpu().numpy()[sub], ref_uv_sub=uv_d.cpu().numpy()[sub], ref_col_sub=col_d.cpu().numpy()[sub],
+        ref_eroded=er.cpu().numpy(), ref_filtered=fl.cpu().numpy(),
+        ref_xyz_map=np.where(g["depth_patch"][..., None] < 0.001, 0, xyzm.cpu().numpy()).astype(np.float32),
+        scores=scores, ref_argmax=np.int32(best))
+    print("wrote", out_path, os.path.getsize(out_path), "bytes; coverage", float((rast[..., 3] > 0).mean()))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", "ref_kernels_golden.npz"))

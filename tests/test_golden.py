@@ -1,0 +1,44 @@
+"""CPU: the oracle against golden vectors produced by the REFERENCE's own CUDA kernels
+(tests/golden/ref_kernels_golden.npz, generated on a B200 by tests/golden/make_golden.py from
+oracle/_ref = vendored nvdiffrast/cudaraster + the reference's depth kernels compiled in place).
+This is what pins the oracle: the reference's test-suite itself holds no vectors for this path."""
+import os
+
+import numpy as np
+
+from oracle import fp_oracle as O
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_kernels_golden.npz"))
+SUB = (slice(0, 160, 4), slice(0, 160, 4))
+
+
+def test_visibility_ids_identical_to_cudaraster():
+    for i in range(G["clip"].shape[0]):
+        ids, nclip = O.rasterize_ids(G["clip"][i], G["faces"])
+        assert nclip == 0
+        assert np.array_equal(ids, G["ref_ids"][i].astype(np.int32)), f"image {i}"
+    assert (G["ref_ids"] > 0).mean() > 0.2
+
+
+def test_shader_interpolate_texture_match_nvdiffrast():
+    for i in range(G["clip"].shape[0]):
+        ids = G["ref_ids"][i].astype(np.int32)
+        rast = O.barycentrics(G["clip"][i], G["faces"], ids)
+        np.testing.assert_allclose(rast[SUB][..., :3], G["ref_bary_sub"][i], atol=2e-4)
+        xyz = O.interpolate(G["pts_cam"][i], G["faces"], rast)
+        np.testing.assert_allclose(xyz[SUB], G["ref_xyz_sub"][i], atol=2e-6)
+        uv = O.interpolate(G["texcoords"], G["faces"], rast)
+        np.testing.assert_allclose(uv[SUB], G["ref_uv_sub"][i], atol=2e-6)
+        col = O.texture_linear(G["texture"], uv)
+        np.testing.assert_allclose(col[SUB], G["ref_col_sub"][i], atol=2e-4)
+
+
+def test_depth_kernels_match_reference():
+    np.testing.assert_array_equal(O.erode_depth(G["depth_patch"]), G["ref_eroded"])
+    np.testing.assert_allclose(O.bilateral_filter_depth(G["ref_eroded"]), G["ref_filtered"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_array_equal(O.depth_to_xyz(G["depth_patch"], G["K"]), G["ref_xyz_map"])
+    assert (G["ref_eroded"] == 0).sum() > (G["depth_patch"] == 0).sum()  # the patch exercises the erosion
+
+
+def test_argmax_matches_thrust_max_element():
+    assert O.argmax_first(G["scores"]) == int(G["ref_argmax"]) == 1  # first of the two equal maxima
