@@ -1,12 +1,12 @@
 // tcgen05 implicit-GEMM convolution kernel (see conv_gemm.h).
 //
-// Roles inside one persistent CTA (192 threads, one CTA per SM):
+// Roles inside one persistent CTA (320 threads, one CTA per SM):
 //   warp 0, lane 0 : TMA producer.  Per k-block (one filter tap x 64 input channels) it loads a
 //                    128-row activation box and a block_n-row weight box into a smem ring.
 //   warp 1, lane 0 : MMA issuer.  Four 128 x block_n x 16 tcgen05.mma per k-block, accumulating in
 //                    one of two TMEM accumulator stages.
-//   warps 2..5     : epilogue.  Each thread owns one output pixel (TMEM lane); reads 32 columns
-//                    at a time with tcgen05.ld and applies bias / residual / ReLU / pos-table.
+//   warps 2..9     : epilogue.  tcgen05.ld 32 columns at a time, transpose through shared memory so
+//                    that global accesses are row-contiguous, bias / residual / ReLU / pos-table.
 // The two TMEM stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "conv_gemm.h"
 
@@ -19,16 +19,17 @@ namespace fpb {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KB
+constexpr int kStageBytesPerWarp = 32 * 32 * 4;         // epilogue staging: 32 rows x 32 fp32 columns
 
 template <int BN>
 struct Cfg {
   static constexpr int kBBytes = BN * kGemmBlockK * 2;
   static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr size_t kSmem =
-      1024 /*alignment slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256 /*barriers*/;
+  static constexpr size_t kSmem = 1024 /*alignment slack*/ + size_t(kStages) * (kABytes + kBBytes) +
+                                  8 * kStageBytesPerWarp /*epilogue staging*/ + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -39,7 +40,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + C::kStages * kABytes;
-  const uint32_t bar_base = b_base + C::kStages * C::kBBytes;
+  const uint32_t stage_base = b_base + C::kStages * C::kBBytes;
+  const uint32_t bar_base = stage_base + 8 * kStageBytesPerWarp;
   // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
@@ -59,7 +61,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      ptx::mbar_init(tempty_bar(s), 128);
+      ptx::mbar_init(tempty_bar(s), 256);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tm_a);
@@ -141,95 +143,123 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;
-    const int rx = row % p.bw;
-    const int ry = (row / p.bw) % p.bh;
-    const int rn = row / (p.bw * p.bh);
+    // Epilogue, 8 warps.  TMEM hands every thread one accumulator ROW (tcgen05.ld 32x32b; warp w may
+    // only read lanes 32*(w%4)..), but global memory wants lanes to cover contiguous bytes of a row.
+    // So each warp stages 32 columns of its 32 rows in shared memory (fp32, XOR-swizzled 16-byte
+    // chunks: conflict-free both ways) and re-reads them with 4 lanes per row: every global
+    // load/store instruction then touches 8 rows x 64 contiguous bytes.  The two warps that share a
+    // TMEM lane quarter take alternate 32-column chunks.
+    const int ew = warp - 2;       // 0..7
+    const int q = warp & 3;        // TMEM lane quarter this warp may read
+    const int chunk_par = ew >> 2; // which of the alternating chunks
+    const uint32_t stg = stage_base + static_cast<uint32_t>(ew) * kStageBytesPerWarp;
+    const int sub = lane >> 2;  // row within a group of 8
+    const int seg = lane & 3;   // 8-column segment of the 32-column chunk
+    // staging addresses (bytes): write = own row, read = rows i*8+sub
+    const uint32_t wr_base = stg + lane * 128;
+    const uint32_t rd_sw = static_cast<uint32_t>(sub & 7);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % p.n_tiles;
       const int mt = tile / p.n_tiles;
-      const int x = (mt % p.tiles_x) * p.bw + rx;
-      const int y = ((mt / p.tiles_x) % p.tiles_y) * p.bh + ry;
-      const int n = (mt / (p.tiles_x * p.tiles_y)) * p.bn + rn;
-      const bool valid = (x < p.W) && (y < p.H) && (n < p.n_img);
+      const int x0 = (mt % p.tiles_x) << p.bw_log2;
+      const int y0 = ((mt / p.tiles_x) % p.tiles_y) << p.bh_log2;
+      const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-
-      const int nn = n % p.img_mod;
-      const int coff = (n / p.img_mod) * p.half_coff + nt * BN;
-      long long opix;
-      if (p.out_phase_split) {
-        const int plane = (y & 1) * 2 + (x & 1);
-        opix = ((static_cast<long long>(nn) * 4 + plane) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) +
-               (x >> 1);
-      } else {
-        opix = (static_cast<long long>(nn) * p.H + y) * p.W + x;
+      // per-lane bookkeeping for the 4 row groups (offsets in units of 8 halves = 16 bytes)
+      uint32_t out_off[4], res_off[4], pp_off[4];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = q * 32 + i * 8 + sub;
+        const int x = x0 + (row & (p.bw - 1));
+        const int y = y0 + ((row >> p.bw_log2) & (p.bh - 1));
+        const int n = n0 + (row >> (p.bw_log2 + p.bh_log2));
+        if ((x < p.W) && (y < p.H) && (n < p.n_img)) vmask |= 1u << i;
+        const int nn = n % p.img_mod;
+        const int coff = (n / p.img_mod) * p.half_coff + nt * BN;
+        long long opix;
+        if (p.out_phase_split) {
+          const int plane = (y & 1) * 2 + (x & 1);
+          opix = ((static_cast<long long>(nn) * 4 + plane) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+        } else {
+          opix = (static_cast<long long>(nn) * p.H + y) * p.W + x;
+        }
+        out_off[i] = static_cast<uint32_t>((opix * p.out_ld + coff) >> 3) + seg;
+        res_off[i] = static_cast<uint32_t>((((static_cast<long long>(n) * p.H + y) * p.W + x) * p.res_ld + nt * BN) >> 3) + seg;
+        pp_off[i] = static_cast<uint32_t>((y * p.W + x) * p.cout + nt * BN) + seg * 8;
       }
-      __half* optr = p.out + opix * p.out_ld + coff;
-      const __half* rptr =
-          p.residual
-              ? p.residual + ((static_cast<long long>(n) * p.H + y) * p.W + x) * p.res_ld + nt * BN
-              : nullptr;
-      const float* pptr =
-          p.post_add ? p.post_add + (static_cast<long long>(y) * p.W + x) * p.cout + nt * BN
-                     : nullptr;
-      const float* bptr = p.bias + nt * BN;
+      const float* bptr = p.bias + nt * BN + seg * 8;
+      uint4* out16 = reinterpret_cast<uint4*>(p.out);
+      const uint4* res16 = reinterpret_cast<const uint4*>(p.residual);
+      const int c_first = chunk_par * 32;
+
+      // The residual rows of a chunk are fetched one chunk ahead (the first one before the wait on
+      // the accumulator), so their DRAM/L2 latency overlaps the TMEM read and the staging.
+      uint4 res_cur[4];
+      auto fetch_residual = [&](uint4 (&dst)[4], int c0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = (res16 && ((vmask >> i) & 1u)) ? __ldg(res16 + res_off[i] + (c0 >> 3)) : make_uint4(0, 0, 0, 0);
+      };
+      fetch_residual(res_cur, c_first);
 
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(taddr + c0, r);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          float v[32];
+      for (int c0 = c_first; c0 < BN; c0 += 64) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bptr + c0 + 4));
+        {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bptr + c0 + j));
-            v[j + 0] = __uint_as_float(r[j + 0]) + b.x;
-            v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
-            v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
-            v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
-          }
-          if (rptr) {
+          for (int c = 0; c < 8; ++c)
+            ptx::st_shared_v4(wr_base + ((c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        }
+        __syncwarp();
+        uint4 res_nxt[4];
+        if (c0 + 64 < BN) fetch_residual(res_nxt, c0 + 64);
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rptr + c0 + j));
-              const __half2* h = reinterpret_cast<const __half2*>(&u);
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t rd = stg + (i * 8 + sub) * 128;
+          float v[8];
+          ptx::ld_shared_v4(rd + (((2 * seg) ^ rd_sw) << 4), v[0], v[1], v[2], v[3]);
+          ptx::ld_shared_v4(rd + (((2 * seg + 1) ^ rd_sw) << 4), v[4], v[5], v[6], v[7]);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          if (res16) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&res_cur[i]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h[e]);
-                v[j + 2 * e] += f.x;
-                v[j + 2 * e + 1] += f.y;
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h2[e]);
+              v[2 * e] += f.x;
+              v[2 * e + 1] += f.y;
             }
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
           }
-          if (pptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(pptr + c0 + j));
-              v[j + 0] += a.x;
-              v[j + 1] += a.y;
-              v[j + 2] += a.z;
-              v[j + 3] += a.w;
-            }
+          if (p.post_add && ((vmask >> i) & 1u)) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.post_add + pp_off[i] + c0));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.post_add + pp_off[i] + c0 + 4));
+            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
           }
+          uint4 u;
+          __half2* h2 = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 u;
-            __half2* h = reinterpret_cast<__half2*>(&u);
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+          if ((vmask >> i) & 1u) out16[out_off[i] + (c0 >> 3)] = u;
+        }
+        __syncwarp();
+        if (c0 + 64 < BN) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-            *reinterpret_cast<uint4*>(optr + c0 + j) = u;
-          }
+          for (int i = 0; i < 4; ++i) res_cur[i] = res_nxt[i];
         }
       }
       ptx::tc_fence_before();
@@ -315,6 +345,7 @@ void taps_stem7_rows(ConvGemmDesc* d) {
 const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   if (const char* e = conv_gemm_init()) return e;
   if (d.bw * d.bh * d.bn != kGemmBlockM) return "conv_gemm: bw*bh*bn must be 128";
+  if ((d.bw & (d.bw - 1)) || (d.bh & (d.bh - 1))) return "conv_gemm: bw and bh must be powers of two";
   if (d.cin % kGemmBlockK != 0) return "conv_gemm: cin must be a multiple of 64";
   if (d.num_taps < 1 || d.num_taps > kMaxTaps) return "conv_gemm: bad tap count";
   int bn_tile = 0;
@@ -366,6 +397,8 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   p.bw = d.bw;
   p.bh = d.bh;
   p.bn = d.bn;
+  for (p.bw_log2 = 0; (1 << p.bw_log2) < d.bw; ++p.bw_log2) {}
+  for (p.bh_log2 = 0; (1 << p.bh_log2) < d.bh; ++p.bh_log2) {}
   p.W = d.out_w;
   p.H = d.out_h;
   p.n_img = d.n_img;

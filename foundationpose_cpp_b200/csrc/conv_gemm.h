@@ -28,6 +28,7 @@ struct ConvGemmParams {
   // M tiling: a tile is bw x bh pixels of bn consecutive images (bw*bh*bn == 128).
   int tiles_x, tiles_y, tiles_img;
   int bw, bh, bn;
+  int bw_log2, bh_log2;
   int W, H, n_img;  // output extent (validity of rows)
   int n_tiles;      // Cout / block_n
   int num_taps;     // filter taps

@@ -102,49 +102,74 @@ __global__ void bilateral_depth_kernel(const float* __restrict__ depth, float* _
 }
 
 // ------------------------------------------------------------------ translation guess
-// GuessTranslation, foundationpose_sampling.cpp:250-298, as one 1024-thread CTA: mask bounding
-// box, then an exact median of the valid depths by 4-pass radix select on the float bit patterns
-// (depths are positive, so the patterns order like the values; the reference uses std::sort).
-__device__ __forceinline__ bool valid_px(const float* d, const uint8_t* m, int i, uint32_t* key) {
-  if (m[i] == 0) return false;
-  const float v = d[i];
-  if (!(v >= kMinDepth)) return false;
-  *key = __float_as_uint(v);
-  return true;
+// GuessTranslation, foundationpose_sampling.cpp:250-298, in two kernels:
+//  (1) mask_scan_kernel (whole grid): mask bounding box (warp-reduced atomics) and compaction of the
+//      valid depths (mask > 0 and depth >= min_depth) into a list (warp-aggregated atomicAdd);
+//  (2) median_select_kernel (one CTA): exact median of the list by 4-pass radix select on the float
+//      bit patterns (depths are positive, so the patterns order like the values; the reference uses
+//      std::sort), then K^-1 back-projection.  meta = {count, umin, umax, vmin, vmax}.
+__global__ void sampler_init_kernel(int* __restrict__ meta) {
+  if (threadIdx.x == 0) {
+    meta[0] = 0;
+    meta[1] = INT_MAX;
+    meta[2] = -1;
+    meta[3] = INT_MAX;
+    meta[4] = -1;
+  }
+}
+
+__global__ void mask_scan_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ mask, int h, int w,
+                                 unsigned* __restrict__ list, int* __restrict__ meta) {
+  const int npx = h * w;
+  const int lane = threadIdx.x & 31;
+  int umin = INT_MAX, umax = -1, vmin = INT_MAX, vmax = -1;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < npx; base += gridDim.x * blockDim.x) {
+    const int i = base + lane;
+    bool valid = false;
+    unsigned key = 0;
+    if (i < npx && mask[i]) {
+      const int v = i / w, u = i - v * w;
+      umin = min(umin, u); umax = max(umax, u); vmin = min(vmin, v); vmax = max(vmax, v);
+      const float d = depth[i];
+      if (d >= kMinDepth) {
+        valid = true;
+        key = __float_as_uint(d);
+      }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
+    if (ballot) {
+      int pos = 0;
+      if (lane == 0) pos = atomicAdd(&meta[0], __popc(ballot));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (valid) list[pos + __popc(ballot & ((1u << lane) - 1u))] = key;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+    umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+    vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  if (lane == 0 && umax >= 0) {
+    atomicMin(&meta[1], umin);
+    atomicMax(&meta[2], umax);
+    atomicMin(&meta[3], vmin);
+    atomicMax(&meta[4], vmax);
+  }
 }
 
 __global__ void __launch_bounds__(1024, 1)
-guess_translation_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ mask, int h,
-                         int w, Intrinsics K, float* __restrict__ center, int* __restrict__ status) {
+median_select_kernel(const unsigned* __restrict__ list, const int* __restrict__ meta, Intrinsics K,
+                     float* __restrict__ center, int* __restrict__ status) {
   __shared__ unsigned hist[256];
-  __shared__ int s_umin, s_umax, s_vmin, s_vmax;
-  __shared__ unsigned s_n, s_prefix, s_rank, s_cnt_less, s_max_less;
+  __shared__ unsigned s_prefix, s_rank, s_cnt_less, s_max_less;
   const int tid = threadIdx.x;
-  const int npx = h * w;
-  if (tid == 0) {
-    s_umin = INT_MAX; s_vmin = INT_MAX; s_umax = -1; s_vmax = -1;
-    s_n = 0; s_cnt_less = 0; s_max_less = 0;
-  }
-  __syncthreads();
-  int umin = INT_MAX, umax = -1, vmin = INT_MAX, vmax = -1;
-  unsigned n = 0;
-  for (int i = tid; i < npx; i += blockDim.x) {
-    if (mask[i]) {
-      const int v = i / w, u = i - v * w;
-      umin = min(umin, u); umax = max(umax, u); vmin = min(vmin, v); vmax = max(vmax, v);
-      uint32_t key;
-      if (valid_px(depth, mask, i, &key)) ++n;
-    }
-  }
-  atomicMin(&s_umin, umin); atomicMax(&s_umax, umax);
-  atomicMin(&s_vmin, vmin); atomicMax(&s_vmax, vmax);
-  atomicAdd(&s_n, n);
-  __syncthreads();
-  if (s_umax < 0) {
+  if (meta[2] < 0) {
     if (tid == 0) atomicOr(status, kStatusEmptyMask);
     return;
   }
-  const unsigned total = s_n;
+  const unsigned total = (unsigned)meta[0];
   if (total == 0) {
     if (tid == 0) atomicOr(status, kStatusNoDepth);
     return;
@@ -152,16 +177,17 @@ guess_translation_kernel(const float* __restrict__ depth, const uint8_t* __restr
   if (tid == 0) {
     s_prefix = 0;
     s_rank = total / 2;  // 0-based rank of the upper median
+    s_cnt_less = 0;
+    s_max_less = 0;
   }
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const unsigned prefix = s_prefix;
     const unsigned himask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (int i = tid; i < npx; i += blockDim.x) {
-      uint32_t key;
-      if (valid_px(depth, mask, i, &key) && (key & himask) == prefix)
-        atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    for (unsigned i = tid; i < total; i += blockDim.x) {
+      const unsigned key = list[i];
+      if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
     if (tid == 0) {
@@ -175,11 +201,11 @@ guess_translation_kernel(const float* __restrict__ depth, const uint8_t* __restr
     }
     __syncthreads();
   }
-  const uint32_t hi_key = s_prefix;
+  const unsigned hi_key = s_prefix;
   unsigned cnt_less = 0, max_less = 0;
-  for (int i = tid; i < npx; i += blockDim.x) {
-    uint32_t key;
-    if (valid_px(depth, mask, i, &key) && key < hi_key) {
+  for (unsigned i = tid; i < total; i += blockDim.x) {
+    const unsigned key = list[i];
+    if (key < hi_key) {
       ++cnt_less;
       max_less = max(max_less, key);
     }
@@ -194,8 +220,8 @@ guess_translation_kernel(const float* __restrict__ depth, const uint8_t* __restr
       const float lo = (s_cnt_less == total / 2) ? __uint_as_float(s_max_less) : hi;
       zc = (lo + hi) / 2.f;
     }
-    const float uc = (float)(s_umin + s_umax) / 2.f;
-    const float vc = (float)(s_vmin + s_vmax) / 2.f;
+    const float uc = (float)(meta[1] + meta[2]) / 2.f;
+    const float vc = (float)(meta[3] + meta[4]) / 2.f;
     for (int r = 0; r < 3; ++r)
       center[r] = ((K.kinv[3 * r] * uc + K.kinv[3 * r + 1] * vc) + K.kinv[3 * r + 2]) * zc;
   }
@@ -285,28 +311,47 @@ __global__ void pose_setup_kernel(const float* __restrict__ poses, int n, Intrin
   aux[i] = a;
 }
 
-// ------------------------------------------------------------------ fused render
-constexpr int kRenderThreads = 512;
+// ------------------------------------------------------------------ render
+constexpr int kRenderThreads = 256;
+constexpr int kRenderTiles = 4;                      // horizontal bands per hypothesis
+constexpr int kTileRows = kCrop / kRenderTiles;      // 40 rows -> 51 KB z-buffer, 4 CTAs per SM
 constexpr unsigned kDepthMin = 2200u << 3;
 constexpr unsigned kDepthMax = 0xFFFFFFFFu - (2200u << 3);
 
-struct ClipV {
-  float x, y, z, w;
-};
-
-__device__ __forceinline__ ClipV clip_vertex(const PoseAux& a, const float* __restrict__ v) {
-  // generate_pose_clip_kernel, foundationpose_render.cu:388-397
-  const float x = v[0], y = v[1], z = v[2];
+// Vertex stage, one thread per (hypothesis, vertex): clip-space position
+// (generate_pose_clip_kernel, foundationpose_render.cu:363-398), camera-space position
+// (transform_points_kernel, :321-341) and headlight diffuse term (transform_normals_kernel, :418-443).
+// The reference keeps these as three [N,V,*] fp32 tensors too (pose_clip, pts_cam, diffuse).
+__global__ void vertex_stage_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all,
+                                    float4* __restrict__ vclip, float4* __restrict__ vattr) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pose = blockIdx.y;
+  if (v >= mesh.num_vertices) return;
+  const PoseAux& a = aux_all[pose];
+  const float x = mesh.vertices[3 * v], y = mesh.vertices[3 * v + 1], z = mesh.vertices[3 * v + 2];
   const float tx = ((a.mvp[0] * x + a.mvp[1] * y) + a.mvp[2] * z) + a.mvp[3];
   const float ty = ((a.mvp[4] * x + a.mvp[5] * y) + a.mvp[6] * z) + a.mvp[7];
   const float tz = ((a.mvp[8] * x + a.mvp[9] * y) + a.mvp[10] * z) + a.mvp[11];
   const float tw = ((a.mvp[12] * x + a.mvp[13] * y) + a.mvp[14] * z) + a.mvp[15];
-  ClipV c;
+  float4 c;
   c.x = tx * a.a00 + tw * a.a30;
   c.y = ty * a.a11 + tw * a.a31;
   c.z = tz;
   c.w = tw;
-  return c;
+  float4 q;
+  q.x = ((a.rot[0] * x + a.rot[1] * y) + a.rot[2] * z) + a.t[0];
+  q.y = ((a.rot[3] * x + a.rot[4] * y) + a.rot[5] * z) + a.t[1];
+  q.z = ((a.rot[6] * x + a.rot[7] * y) + a.rot[8] * z) + a.t[2];
+  const float nx0 = mesh.normals[3 * v], ny0 = mesh.normals[3 * v + 1], nz0 = mesh.normals[3 * v + 2];
+  const float nx = (a.rot[0] * nx0 + a.rot[1] * ny0) + a.rot[2] * nz0;
+  const float ny = (a.rot[3] * nx0 + a.rot[4] * ny0) + a.rot[5] * nz0;
+  const float nz = (a.rot[6] * nx0 + a.rot[7] * ny0) + a.rot[8] * nz0;
+  const float l2 = sqrtf((nx * nx + ny * ny) + nz * nz);
+  const float val = l2 == 0.f ? 0.f : -nz / l2;
+  q.w = fminf(fmaxf(val, 0.f), 1.f);
+  const long long o = (long long)pose * mesh.num_vertices + v;
+  vclip[o] = c;
+  vattr[o] = q;
 }
 
 __device__ __forceinline__ int snap(float v) {
@@ -341,36 +386,34 @@ __device__ __forceinline__ void setup_pleq(float z0, float z1, float z2, int v0x
   pl[2] = z;
 }
 
-// One CTA per hypothesis.  Phase 1: every thread takes triangles, does cudaraster's triangle
-// setup (TriangleSetup.inl fast path) and resolves visibility with a 64-bit atomicMin on a
-// shared-memory z-buffer whose key is (u32 depth << 32) | ~triangle, i.e. nearest wins and on equal
-// depth the later triangle wins (FineRaster.inl:152-172,338-351).  Phase 2: per pixel, nvdiffrast's
-// barycentrics / interpolation / texture (rasterize.cu:55-89, interpolate.cu:46-76,
+// One CTA per (band of 40 rows, hypothesis).  Phase 1: every thread takes triangles, does
+// cudaraster's triangle setup (TriangleSetup.inl fast path) and resolves visibility with a 64-bit
+// atomicMin on a shared-memory z-buffer whose key is (u32 depth << 32) | ~triangle, i.e. nearest wins
+// and on equal depth the later triangle wins (FineRaster.inl:152-172,338-351).  Phase 2: per pixel,
+// nvdiffrast's barycentrics / interpolation / texture (rasterize.cu:55-89, interpolate.cu:46-76,
 // texture.cu:19-96), the reference's shading (foundationpose_render.cu:459-501), vertical flip
 // (foundationpose_render.cpp:676-680), normalisation and packing (foundationpose_render.cu:61-140).
-__global__ void __launch_bounds__(kRenderThreads, 1)
-render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, __half* __restrict__ packed,
-              int img0, int32_t* __restrict__ rast_id_debug, int* __restrict__ status) {
-  extern __shared__ unsigned long long zbuf[];  // [160*160]
-  __shared__ PoseAux a;
-  const int pose = blockIdx.x;
-  if (threadIdx.x < sizeof(PoseAux) / 4)
-    reinterpret_cast<float*>(&a)[threadIdx.x] = reinterpret_cast<const float*>(aux_all + pose)[threadIdx.x];
-  for (int i = threadIdx.x; i < kCrop * kCrop; i += blockDim.x) zbuf[i] = ~0ull;
+__global__ void __launch_bounds__(kRenderThreads, 4)
+render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vclip,
+              const float4* __restrict__ vattr, __half* __restrict__ packed, int img0,
+              int32_t* __restrict__ rast_id_debug, int* __restrict__ status) {
+  extern __shared__ unsigned long long zbuf[];  // [kTileRows * 160]
+  const int pose = blockIdx.y;
+  const int row0 = blockIdx.x * kTileRows;  // GL rows [row0, row0 + kTileRows)
+  for (int i = threadIdx.x; i < kCrop * kTileRows; i += blockDim.x) zbuf[i] = ~0ull;
   __syncthreads();
 
   constexpr int W = kCrop, H = kCrop;
   const float vs = (float)(W << 3);
   constexpr int bias = (W - 1) << 3;  // sample x of pixel px = px*16 - bias
+  const float4* pc = vclip + (long long)pose * mesh.num_vertices;
   bool clip_path = false;
   for (int t = threadIdx.x; t < mesh.num_faces; t += blockDim.x) {
     const int i0 = mesh.faces[3 * t], i1 = mesh.faces[3 * t + 1], i2 = mesh.faces[3 * t + 2];
     if ((unsigned)i0 >= (unsigned)mesh.num_vertices || (unsigned)i1 >= (unsigned)mesh.num_vertices ||
         (unsigned)i2 >= (unsigned)mesh.num_vertices)
       continue;
-    const ClipV A = clip_vertex(a, mesh.vertices + 3 * i0);
-    const ClipV B = clip_vertex(a, mesh.vertices + 3 * i1);
-    const ClipV C = clip_vertex(a, mesh.vertices + 3 * i2);
+    const float4 A = pc[i0], B = pc[i1], C = pc[i2];
     if ((A.w < fabsf(A.x)) | (A.w < fabsf(A.y)) | (A.w < fabsf(A.z))) {
       if (((A.w < +A.x) & (B.w < +B.x) & (C.w < +C.x)) | ((A.w < -A.x) & (B.w < -B.x) & (C.w < -C.x)) |
           ((A.w < +A.y) & (B.w < +B.y) & (C.w < +C.y)) | ((A.w < -A.y) & (B.w < -B.y) & (C.w < -C.y)) |
@@ -392,6 +435,9 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, __half* __re
       clip_path = true;
       continue;
     }
+    const int px0 = max((lox + bias + 15) >> 4, 0), px1 = min((hix + bias) >> 4, W - 1);
+    const int py0 = max((loy + bias + 15) >> 4, row0), py1 = min((hiy + bias) >> 4, row0 + kTileRows - 1);
+    if (px0 > px1 || py0 > py1) continue;  // no sample of this band inside the bounding box
     int d1x = p1x - p0x, d1y = p1y - p0y, d2x = p2x - p0x, d2y = p2y - p0y;
     int area = d1x * d2y - d1y * d2x;
     if (area == 0) continue;
@@ -414,8 +460,6 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, __half* __re
     unsigned pl[3];
     setup_pleq(zv0, zv1, zv2, p0x + (W << 3) - 8, p0y + (H << 3) - 8, d1x, d1y, d2x, d2y,
                1.0f / (float)area, pl);
-    const int px0 = max((lox + bias + 15) >> 4, 0), px1 = min((hix + bias) >> 4, W - 1);
-    const int py0 = max((loy + bias + 15) >> 4, 0), py1 = min((hiy + bias) >> 4, H - 1);
     const int e0x = d1x, e0y = d1y, e1x = d2x - d1x, e1y = d2y - d1y, e2x = -d2x, e2y = -d2y;
     const long long adj0 = (e0y > 0 || (e0y == 0 && e0x <= 0)) ? 1 : 0;
     const long long adj1 = (e1y > 0 || (e1y == 0 && e1x <= 0)) ? 1 : 0;
@@ -431,7 +475,7 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, __half* __re
         if ((v0 | v1 | v2) < 0) continue;
         const unsigned depth = pl[0] * (unsigned)px + pl[1] * (unsigned)py + pl[2];
         if (depth > kDepthMax) continue;  // behind the cleared depth (FineRaster.inl:338)
-        atomicMin(&zbuf[py * W + px], ((unsigned long long)depth << 32) | low);
+        atomicMin(&zbuf[(py - row0) * W + px], ((unsigned long long)depth << 32) | low);
       }
     }
   }
@@ -442,19 +486,20 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, __half* __re
   const float xs = 2.0f / (float)W, xo = 1.0f / (float)W - 1.0f;
   const float ys = 2.0f / (float)H, yo = 1.0f / (float)H - 1.0f;
   const float half_d = mesh.diameter / 2.f;
+  const float4* pa = vattr + (long long)pose * mesh.num_vertices;
+  const float t_x = aux_all[pose].t[0], t_y = aux_all[pose].t[1], t_z = aux_all[pose].t[2];
   __half* img = packed + (long long)(img0 + pose) * kPackImageElems;
-  for (int i = threadIdx.x; i < W * H; i += blockDim.x) {
-    const int py = i / W, px = i - py * W;
+  for (int i = threadIdx.x; i < W * kTileRows; i += blockDim.x) {
+    const int ly = i / W, px = i - ly * W;
+    const int py = row0 + ly;
     const unsigned long long key = zbuf[i];
     const int tri = key == ~0ull ? -1 : (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
-    if (rast_id_debug) rast_id_debug[(long long)pose * W * H + i] = tri + 1;
+    if (rast_id_debug) rast_id_debug[(long long)pose * W * H + py * W + px] = tri + 1;
     float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (tri >= 0) {
       const int i0 = mesh.faces[3 * tri], i1 = mesh.faces[3 * tri + 1], i2 = mesh.faces[3 * tri + 2];
-      const float* v0 = mesh.vertices + 3 * i0;
-      const float* v1 = mesh.vertices + 3 * i1;
-      const float* v2 = mesh.vertices + 3 * i2;
-      const ClipV p0 = clip_vertex(a, v0), p1 = clip_vertex(a, v1), p2 = clip_vertex(a, v2);
+      const float4 p0 = pc[i0], p1 = pc[i1], p2 = pc[i2];
+      const float4 q0 = pa[i0], q1 = pa[i1], q2 = pa[i2];
       const float fx = xs * (float)px + xo;
       const float fy = ys * (float)py + yo;
       const float p0x = p0.x - fx * p0.w, p0y = p0.y - fy * p0.w;
@@ -467,38 +512,15 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, __half* __re
       const float b0 = __saturatef(a0 * iw);
       const float b1 = __saturatef(a1 * iw);
       const float b2 = (1.f - b0) - b1;
-      // xyz in the camera frame (transform_points_kernel + interpolate)
-      float xyz[3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const float q0 = ((a.rot[3 * r] * v0[0] + a.rot[3 * r + 1] * v0[1]) + a.rot[3 * r + 2] * v0[2]) + a.t[r];
-        const float q1 = ((a.rot[3 * r] * v1[0] + a.rot[3 * r + 1] * v1[1]) + a.rot[3 * r + 2] * v1[2]) + a.t[r];
-        const float q2 = ((a.rot[3 * r] * v2[0] + a.rot[3 * r + 1] * v2[1]) + a.rot[3 * r + 2] * v2[2]) + a.t[r];
-        xyz[r] = (b0 * q0 + b1 * q1) + b2 * q2;
-      }
-      // texcoords
-      const float* t0 = mesh.texcoords + 2 * i0;
-      const float* t1 = mesh.texcoords + 2 * i1;
-      const float* t2 = mesh.texcoords + 2 * i2;
-      float u = (b0 * t0[0] + b1 * t1[0]) + b2 * t2[0];
-      float v = (b0 * t0[1] + b1 * t1[1]) + b2 * t2[1];
-      // diffuse (transform_normals_kernel + interpolate)
-      float dif;
-      {
-        float dv[3];
-        const int vi[3] = {i0, i1, i2};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float* nrm = mesh.normals + 3 * vi[k];
-          const float nx = (a.rot[0] * nrm[0] + a.rot[1] * nrm[1]) + a.rot[2] * nrm[2];
-          const float ny = (a.rot[3] * nrm[0] + a.rot[4] * nrm[1]) + a.rot[5] * nrm[2];
-          const float nz = (a.rot[6] * nrm[0] + a.rot[7] * nrm[1]) + a.rot[8] * nrm[2];
-          const float l2 = sqrtf((nx * nx + ny * ny) + nz * nz);
-          const float val = l2 == 0.f ? 0.f : -nz / l2;
-          dv[k] = fminf(fmaxf(val, 0.f), 1.f);
-        }
-        dif = (b0 * dv[0] + b1 * dv[1]) + b2 * dv[2];
-      }
+      const float xyz0 = (b0 * q0.x + b1 * q1.x) + b2 * q2.x;
+      const float xyz1 = (b0 * q0.y + b1 * q1.y) + b2 * q2.y;
+      const float xyz2 = (b0 * q0.z + b1 * q1.z) + b2 * q2.z;
+      const float dif = (b0 * q0.w + b1 * q1.w) + b2 * q2.w;
+      const float2 t0 = *reinterpret_cast<const float2*>(mesh.texcoords + 2 * i0);
+      const float2 t1 = *reinterpret_cast<const float2*>(mesh.texcoords + 2 * i1);
+      const float2 t2 = *reinterpret_cast<const float2*>(mesh.texcoords + 2 * i2);
+      float u = (b0 * t0.x + b1 * t1.x) + b2 * t2.x;
+      float v = (b0 * t0.y + b1 * t1.y) + b2 * t2.y;
       // bilinear texture fetch, wrap
       const int tw = mesh.tex_w, th = mesh.tex_h;
       u = u - floorf(u);
@@ -525,12 +547,11 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, __half* __re
         o[ch] = fminf(fmaxf(col * light, 0.f), 1.f);
       }
       // normalise (threshold_and_downscale_pointcloud_kernel)
-      const bool invalid = xyz[2] < kMinDepth;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const float q = (xyz[r] - a.t[r]) / half_d;
-        o[3 + r] = (invalid || fabsf(q) > kMaxDepth) ? 0.f : q;
-      }
+      const bool invalid = xyz2 < kMinDepth;
+      const float qx = (xyz0 - t_x) / half_d, qy = (xyz1 - t_y) / half_d, qz = (xyz2 - t_z) / half_d;
+      o[3] = (invalid || fabsf(qx) > kMaxDepth) ? 0.f : qx;
+      o[4] = (invalid || fabsf(qy) > kMaxDepth) ? 0.f : qy;
+      o[5] = (invalid || fabsf(qz) > kMaxDepth) ? 0.f : qz;
     }
     const int yimg = H - 1 - py;
     uint4 pk;
@@ -607,7 +628,7 @@ __global__ void warp_kernel(const uint8_t* __restrict__ rgb, const float* __rest
 
 const char* preprocess_init() {
   cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kCrop * kCrop * 8);
+                                       kCrop * kTileRows * 8);
   return e == cudaSuccess ? nullptr : "cudaFuncSetAttribute(render_kernel smem) failed";
 }
 
@@ -623,8 +644,14 @@ void launch_depth_filters(const float* depth, float* eroded, float* filtered, in
 }
 
 void launch_guess_translation(const float* filtered, const uint8_t* mask, int h, int w, const Intrinsics& K,
-                              float* center, int* status, unsigned*, cudaStream_t s) {
-  guess_translation_kernel<<<1, 1024, 0, s>>>(filtered, mask, h, w, K, center, status);
+                              float* center, int* status, unsigned* scratch, cudaStream_t s) {
+  // scratch: [8] ints of meta followed by h*w list entries
+  int* meta = reinterpret_cast<int*>(scratch);
+  unsigned* list = scratch + 8;
+  sampler_init_kernel<<<1, 32, 0, s>>>(meta);
+  const int blocks = (h * w + 1023) / 1024;
+  mask_scan_kernel<<<blocks, 256, 0, s>>>(filtered, mask, h, w, list, meta);
+  median_select_kernel<<<1, 1024, 0, s>>>(list, meta, K, center, status);
 }
 
 void launch_fill_hypotheses(const float* grid, const float* center, float* poses, int n, cudaStream_t s) {
@@ -636,10 +663,12 @@ void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float dia
   pose_setup_kernel<<<(n + 63) / 64, 64, 0, s>>>(poses, n, K, diameter, crop_ratio, aux);
 }
 
-void launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, __half* packed, int img0,
-                   int32_t* rast_id_debug, int* status, cudaStream_t s) {
+void launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr, __half* packed,
+                   int img0, int32_t* rast_id_debug, int* status, cudaStream_t s) {
   if (n <= 0) return;
-  render_kernel<<<n, kRenderThreads, kCrop * kCrop * 8, s>>>(mesh, aux, packed, img0, rast_id_debug, status);
+  vertex_stage_kernel<<<dim3((mesh.num_vertices + 255) / 256, n), 256, 0, s>>>(mesh, aux, vclip, vattr);
+  render_kernel<<<dim3(kRenderTiles, n), kRenderThreads, kCrop * kTileRows * 8, s>>>(mesh, aux, vclip, vattr, packed,
+                                                                                      img0, rast_id_debug, status);
 }
 
 void launch_warp(const uint8_t* rgb, const float* xyz, int h, int w, const PoseAux* aux, int n, float diameter,

@@ -53,6 +53,7 @@ void launch_depth_to_xyz(const float* depth, float* xyz, int h, int w, const Int
 void launch_depth_filters(const float* depth, float* eroded, float* filtered, int h, int w,
                           cudaStream_t s);
 // Mask bounding box + median depth + K^-1 back-projection; writes center[3] and status.
+// scratch: 8 + h*w 32-bit words.
 void launch_guess_translation(const float* filtered, const uint8_t* mask, int h, int w,
                               const Intrinsics& K, float* center, int* status, unsigned* scratch,
                               cudaStream_t s);
@@ -61,9 +62,10 @@ void launch_fill_hypotheses(const float* grid, const float* center, float* poses
                             cudaStream_t s);
 void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float diameter,
                        float crop_ratio, PoseAux* aux, cudaStream_t s);
-// Rasterise + shade + flip + normalise + pack hypothesis i into packed image `img0 + i`.
-void launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, __half* packed, int img0,
-                   int32_t* rast_id_debug, int* status, cudaStream_t s);
+// Vertex stage + rasterise + shade + flip + normalise + pack hypothesis i into packed image
+// `img0 + i`.  vclip / vattr: scratch of n * num_vertices float4 each.
+void launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr,
+                   __half* packed, int img0, int32_t* rast_id_debug, int* status, cudaStream_t s);
 // Crop/warp the observed rgb + xyz, normalise, pack into packed image `img0 + i`.
 void launch_warp(const uint8_t* rgb, const float* xyz, int h, int w, const PoseAux* aux, int n,
                  float diameter, __half* packed, int img0, cudaStream_t s);

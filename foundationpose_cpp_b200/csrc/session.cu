@@ -171,8 +171,10 @@ struct fpb200_session {
   DevBuf<float> depth, xyz, eroded, filtered, grid, poses, center, exch_local, exch_all, feats, tail_qkv,
       tail_att, tail_out, scores, trans, rot, best_pose, all_poses;
   DevBuf<int> status, best_index;
+  DevBuf<unsigned> sampler_scratch;
   DevBuf<int32_t> rast_id;
   DevBuf<PoseAux> aux;
+  DevBuf<float4> vclip, vattr;  // vertex-stage output [local hypotheses][max vertices]
   HostResult* host_result = nullptr;  // pinned
   std::unique_ptr<Arena> arena;
   std::unique_ptr<Network> refiner, scorer;
@@ -263,10 +265,11 @@ void do_sample(fpb200_session* s, const uint8_t* mask, MeshEntry* mesh) {
   }
   FPB_REQUIRE(s->mask_resident, "mask must not be null (no mask is resident on the device yet)");
   launch_depth_filters(s->depth.p, s->eroded.p, s->filtered.p, h, w, s->stream);
-  launch_guess_translation(s->filtered.p, s->mask.p, h, w, s->intr, s->center.p, s->status.p, nullptr, s->stream);
+  launch_guess_translation(s->filtered.p, s->mask.p, h, w, s->intr, s->center.p, s->status.p, s->sampler_scratch.p,
+                           s->stream);
   const int n = std::min(kGridPoses, s->opt.max_hyps);
   launch_fill_hypotheses(s->grid.p, s->center.p, s->poses.p, n, s->stream);
-  s->count_launches(4);
+  s->count_launches(6);
   s->cur_mesh = mesh;
   s->set_shard(n);
   s->mark(2);
@@ -277,9 +280,9 @@ void do_render_and_transform(fpb200_session* s, float crop_ratio) {
   const int nl = s->hi - s->lo;
   const MeshEntry& m = *s->cur_mesh;
   launch_pose_setup(s->poses.p + 16 * s->lo, nl, s->intr, m.dm.diameter, crop_ratio, s->aux.p, s->stream);
-  launch_render(m.dm, s->aux.p, nl, s->arena->packed, 0, s->rast_id.p, s->status.p, s->stream);
+  launch_render(m.dm, s->aux.p, nl, s->vclip.p, s->vattr.p, s->arena->packed, 0, s->rast_id.p, s->status.p, s->stream);
   launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->stream);
-  s->count_launches(3);
+  s->count_launches(4);
   s->crop_ratio_last = crop_ratio;
 }
 
@@ -471,7 +474,7 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
     const size_t px = (size_t)max_h * max_w;
     const int cap = s->opt.max_hyps;
     s->rgb.alloc(px * 3); s->mask.alloc(px); s->depth.alloc(px); s->xyz.alloc(px * 3);
-    s->eroded.alloc(px); s->filtered.alloc(px);
+    s->eroded.alloc(px); s->filtered.alloc(px); s->sampler_scratch.alloc(px + 8);
     const std::vector<float> grid = make_rotation_grid();
     s->grid.upload(grid.data(), grid.size());
     s->poses.alloc((size_t)cap * 16); s->all_poses.alloc((size_t)cap * 16);
@@ -484,6 +487,12 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
     s->rot.alloc((size_t)cap * 3);
     FPB_CUDA(cudaMemset(s->status.p, 0, sizeof(int)));
     const int local_cap = (cap + s->opt.shard_world - 1) / s->opt.shard_world;
+    {
+      size_t max_v = 0;
+      for (auto& m : s->meshes) max_v = std::max(max_v, (size_t)m->dm.num_vertices);
+      s->vclip.alloc((size_t)local_cap * max_v);
+      s->vattr.alloc((size_t)local_cap * max_v);
+    }
     s->arena.reset(new Arena(local_cap));
     s->refiner.reset(new Network(NetKind::kRefiner, refiner_weights, s->arena.get()));
     s->scorer.reset(new Network(NetKind::kScorer, scorer_weights, s->arena.get()));

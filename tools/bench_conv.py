@@ -34,7 +34,10 @@ def main():
         ("lin 512->1536", 1, n * 400, 512, 1536, (128, 1, 1), capi.TAPS_1X1),
         ("lin 512->512", 1, n * 400, 512, 512, (128, 1, 1), capi.TAPS_1X1),
     ]
-    for name, imgs, hw, cin, cout, tile, kind in cases:
+    only = os.environ.get("FPB_CASE")
+    for ci, (name, imgs, hw, cin, cout, tile, kind) in enumerate(cases):
+        if only is not None and str(ci) not in only.split(","):
+            continue
         d = capi.ConvDesc()
         if kind == capi.TAPS_STEM7_ROWS:
             x = torch.randn(imgs * 160 * layouts.STEM_PITCH * 8 + 4096, device="cuda").half()
