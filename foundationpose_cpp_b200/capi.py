@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
         ("post_add", C.c_void_p),
         ("out", C.c_void_p),
         ("relu", C.c_int), ("out_phase_split", C.c_int), ("out_ld", C.c_int), ("img_mod", C.c_int),
-        ("half_coff", C.c_int), ("max_ctas", C.c_int),
+        ("half_coff", C.c_int), ("max_ctas", C.c_int), ("cluster", C.c_int),
     ]
 
 

@@ -11,6 +11,7 @@
 #include "conv_gemm.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ptx.cuh"
@@ -32,7 +33,10 @@ struct Cfg {
                                   8 * kStageBytesPerWarp /*epilogue staging*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// CS = cluster size: the CS CTAs of a cluster work on CS consecutive M tiles of the same N tile in
+// lock step; each loads 1/CS of the weight tile and multicasts it to all, so the L2 -> SM traffic
+// per CTA and k-block drops from A + B to A + B/CS.
+template <int BN, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN>;
@@ -57,7 +61,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), CS);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
@@ -73,20 +77,26 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync();  // peers' barriers are initialised before anything is multicast
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_img;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int m_groups = (m_tiles + CS - 1) / CS;
+  const int total_tiles = m_groups * p.n_tiles;  // work items of a cluster
   const int kblocks = p.num_taps * p.cblocks;
+  const int crank = CS > 1 ? (int)ptx::cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CS;
+  const int num_clusters = gridDim.x / CS;
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CS) - 1u);
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int nt = tile % p.n_tiles;
-        const int mt = tile / p.n_tiles;
+        const int mt = (tile / p.n_tiles) * CS + crank;  // may be >= m_tiles: TMA zero-fills, epilogue masks
         const int x0 = (mt % p.tiles_x) * p.bw;
         const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
         const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
@@ -100,8 +110,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             ptx::mbar_expect_tx(full_bar(stage), kABytes + C::kBBytes);
             ptx::tma_load_5d(a_base + stage * kABytes, &p.tm_a, full_bar(stage), cb * kGemmBlockK,
                              cx, cy, cp, n0);
-            ptx::tma_load_2d(b_base + stage * C::kBBytes, &p.tm_b, full_bar(stage),
-                             kb * kGemmBlockK, nt * BN);
+            if (CS == 1) {
+              ptx::tma_load_2d(b_base + stage * C::kBBytes, &p.tm_b, full_bar(stage), kb * kGemmBlockK, nt * BN);
+            } else {
+              ptx::tma_load_2d_mcast(b_base + stage * C::kBBytes + crank * (C::kBBytes / CS), &p.tm_b,
+                                     full_bar(stage), kb * kGemmBlockK, nt * BN + crank * (BN / CS), kAllCtas);
+            }
             if (++stage == C::kStages) {
               stage = 0;
               phase ^= 1u;
@@ -116,7 +130,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -133,7 +147,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             // descriptor's 16-byte address units
             ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
           }
-          ptx::umma_commit(empty_bar(stage));
+          if (CS == 1) ptx::umma_commit(empty_bar(stage));
+          else ptx::umma_commit_mcast(empty_bar(stage), kAllCtas);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -159,9 +174,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint32_t wr_base = stg + lane * 128;
     const uint32_t rd_sw = static_cast<uint32_t>(sub & 7);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       const int nt = tile % p.n_tiles;
-      const int mt = tile / p.n_tiles;
+      const int mt = (tile / p.n_tiles) * CS + crank;
       const int x0 = (mt % p.tiles_x) << p.bw_log2;
       const int y0 = ((mt / p.tiles_x) % p.tiles_y) << p.bh_log2;
       const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
@@ -269,6 +284,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync();  // no CTA exits while a peer may still signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::kTmemCols);
@@ -291,14 +307,16 @@ const char* conv_gemm_init() {
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
     return "cuTensorMapEncodeTiled not available from the CUDA driver";
-  e = cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)Cfg<64>::kSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)Cfg<128>::kSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)Cfg<256>::kSmem);
+  e = cudaSuccess;
+  auto set_attr = [&](auto kernel, size_t smem) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  };
+  set_attr(conv_gemm_kernel<64, 1>, Cfg<64>::kSmem);
+  set_attr(conv_gemm_kernel<128, 1>, Cfg<128>::kSmem);
+  set_attr(conv_gemm_kernel<256, 1>, Cfg<256>::kSmem);
+  set_attr(conv_gemm_kernel<64, 2>, Cfg<64>::kSmem);
+  set_attr(conv_gemm_kernel<128, 2>, Cfg<128>::kSmem);
+  set_attr(conv_gemm_kernel<256, 2>, Cfg<256>::kSmem);
   if (e != cudaSuccess) return "cudaFuncSetAttribute(max dynamic smem) failed (not an sm_100a device?)";
   int dev = 0;
   cudaGetDevice(&dev);
@@ -357,6 +375,14 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   if (out_ld % 8 || d.half_coff % 8) return "conv_gemm: output leading dims must be multiples of 8";
   if (d.out_phase_split && ((d.out_h | d.out_w) & 1)) return "conv_gemm: phase-split needs even H, W";
 
+  // cluster size: pairs of CTAs share the weight tile by multicast when there is enough work
+  const long long m_tiles_all = (long long)((d.out_w + d.bw - 1) / d.bw) * ((d.out_h + d.bh - 1) / d.bh) *
+                                ((d.n_img + d.bn - 1) / d.bn);
+  // (measured on B200: multicast pays for the 256-wide tiles only; narrower tiles are bound by the
+  // SM's shared-memory fill rate, which multicast does not reduce)
+  int cluster = d.cluster > 0 ? d.cluster : ((m_tiles_all >= 2 * g_num_sms && d.cout % 256 == 0) ? 2 : 1);
+  if (const char* env = getenv("FPB_GEMM_CLUSTER")) cluster = atoi(env) == 1 ? 1 : 2;
+  if (cluster != 1 && cluster != 2) return "conv_gemm: cluster must be 1 or 2";
   ConvGemmParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   {
@@ -382,7 +408,7 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
     const long long ktot = (long long)d.num_taps * d.cin;
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d.cout};
     cuuint64_t strides[1] = {(cuuint64_t)(ktot * 2)};
-    cuuint32_t box[2] = {kGemmBlockK, (cuuint32_t)bn_tile};
+    cuuint32_t box[2] = {kGemmBlockK, (cuuint32_t)(bn_tile / cluster)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = g_encode(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)d.weight, dims,
                           strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -424,28 +450,43 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   p.half_coff = d.half_coff;
 
   plan->block_n = bn_tile;
-  const long long tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles;
-  const int cap = d.max_ctas > 0 ? d.max_ctas : g_num_sms;
-  plan->grid = (int)(tiles < cap ? tiles : cap);
+  plan->cluster = cluster;
+  const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_img;
+  const long long work = ((m_tiles + cluster - 1) / cluster) * p.n_tiles;  // per cluster
+  const int cap = (d.max_ctas > 0 ? d.max_ctas : g_num_sms) / cluster;
+  plan->grid = (int)(work < cap ? work : cap) * cluster;
   plan->smem = bn_tile == 256 ? Cfg<256>::kSmem : (bn_tile == 128 ? Cfg<128>::kSmem : Cfg<64>::kSmem);
   plan->flops = 2.0 * d.n_img * d.out_h * d.out_w * (double)d.cout * d.num_taps * d.cin;
   return nullptr;
 }
 
+namespace {
+template <int BN, int CS>
+cudaError_t launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CS>, plan.p);
+}
+}  // namespace
+
 cudaError_t launch_conv_gemm(const ConvGemmPlan& plan, cudaStream_t stream) {
   if (plan.grid <= 0) return cudaSuccess;
+  const bool pair = plan.cluster == 2;
   switch (plan.block_n) {
-    case 256:
-      conv_gemm_kernel<256><<<plan.grid, kThreads, plan.smem, stream>>>(plan.p);
-      break;
-    case 128:
-      conv_gemm_kernel<128><<<plan.grid, kThreads, plan.smem, stream>>>(plan.p);
-      break;
-    default:
-      conv_gemm_kernel<64><<<plan.grid, kThreads, plan.smem, stream>>>(plan.p);
-      break;
+    case 256: return pair ? launch_one<256, 2>(plan, stream) : launch_one<256, 1>(plan, stream);
+    case 128: return pair ? launch_one<128, 2>(plan, stream) : launch_one<128, 1>(plan, stream);
+    default: return pair ? launch_one<64, 2>(plan, stream) : launch_one<64, 1>(plan, stream);
   }
-  return cudaGetLastError();
 }
 
 }  // namespace fpb

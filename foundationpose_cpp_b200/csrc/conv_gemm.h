@@ -72,11 +72,13 @@ struct ConvGemmDesc {
   int img_mod = 0;  // 0 -> n_img
   int half_coff = 0;
   int max_ctas = 0;  // 0 -> number of SMs
+  int cluster = 0;   // CTAs sharing a weight tile by TMA multicast: 1 or 2 (0 -> automatic)
 };
 
 struct ConvGemmPlan {
   ConvGemmParams p;
   int block_n = 0;
+  int cluster = 1;
   int grid = 0;
   size_t smem = 0;
   double flops = 0;  // 2*M*N*K over valid rows

@@ -46,6 +46,7 @@ extern "C" int fpb200_debug_conv_gemm(const fpb200_conv_desc* c, int repeat, flo
     d.img_mod = c->img_mod;
     d.half_coff = c->half_coff;
     d.max_ctas = c->max_ctas;
+    d.cluster = c->cluster;
     ConvGemmPlan plan;
     if (const char* e = build_conv_gemm(d, &plan)) return fail(FPB200_ERR_INVALID, "%s", e);
     cudaEvent_t e0, e1;

@@ -408,21 +408,36 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4
   constexpr int bias = (W - 1) << 3;  // sample x of pixel px = px*16 - bias
   const float4* pc = vclip + (long long)pose * mesh.num_vertices;
   bool clip_path = false;
-  for (int t = threadIdx.x; t < mesh.num_faces; t += blockDim.x) {
-    const int i0 = mesh.faces[3 * t], i1 = mesh.faces[3 * t + 1], i2 = mesh.faces[3 * t + 2];
-    if ((unsigned)i0 >= (unsigned)mesh.num_vertices || (unsigned)i1 >= (unsigned)mesh.num_vertices ||
-        (unsigned)i2 >= (unsigned)mesh.num_vertices)
-      continue;
-    const float4 A = pc[i0], B = pc[i1], C = pc[i2];
-    if ((A.w < fabsf(A.x)) | (A.w < fabsf(A.y)) | (A.w < fabsf(A.z))) {
+  // Warp-uniform trip count and a single `live` flag instead of `continue`s: the lanes of a warp
+  // reconverge at every iteration (with early exits the compiler let them drift apart and the loop
+  // ran with ~6 active lanes).
+  const int n_iter = (mesh.num_faces + blockDim.x - 1) / blockDim.x;
+  for (int it = 0; it < n_iter; ++it) {
+    const int t = it * blockDim.x + threadIdx.x;
+    bool live = t < mesh.num_faces;
+    int i0 = 0, i1 = 0, i2 = 0;
+    if (live) {
+      i0 = mesh.faces[3 * t];
+      i1 = mesh.faces[3 * t + 1];
+      i2 = mesh.faces[3 * t + 2];
+      live = (unsigned)i0 < (unsigned)mesh.num_vertices && (unsigned)i1 < (unsigned)mesh.num_vertices &&
+             (unsigned)i2 < (unsigned)mesh.num_vertices;
+    }
+    float4 A = make_float4(0.f, 0.f, 0.f, 1.f), B = A, C = A;
+    if (live) {
+      A = pc[i0];
+      B = pc[i1];
+      C = pc[i2];
+    }
+    if (live && ((A.w < fabsf(A.x)) | (A.w < fabsf(A.y)) | (A.w < fabsf(A.z)))) {
       if (((A.w < +A.x) & (B.w < +B.x) & (C.w < +C.x)) | ((A.w < -A.x) & (B.w < -B.x) & (C.w < -C.x)) |
           ((A.w < +A.y) & (B.w < +B.y) & (C.w < +C.y)) | ((A.w < -A.y) & (B.w < -B.y) & (C.w < -C.y)) |
           ((A.w < +A.z) & (B.w < +B.z) & (C.w < +C.z)) | ((A.w < -A.z) & (B.w < -B.z) & (C.w < -C.z)))
-        continue;
+        live = false;
     }
-    if (!((A.w >= fabsf(A.z)) & (B.w >= fabsf(B.z)) & (C.w >= fabsf(C.z)))) {
+    if (live && !((A.w >= fabsf(A.z)) & (B.w >= fabsf(B.z)) & (C.w >= fabsf(C.z)))) {
       clip_path = true;  // cudaraster would clip this triangle against the near/far plane
-      continue;
+      live = false;
     }
     float rw0 = 1.0f / A.w, rw1 = 1.0f / B.w, rw2 = 1.0f / C.w;
     int p0x = snap(A.x * rw0 * vs), p0y = snap(A.y * rw0 * vs);
@@ -430,54 +445,58 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4
     int p2x = snap(C.x * rw2 * vs), p2y = snap(C.y * rw2 * vs);
     const int lox = min3(p0x, p1x, p2x), loy = min3(p0y, p1y, p2y);
     const int hix = max3(p0x, p1x, p2x), hiy = max3(p0y, p1y, p2y);
-    if (!(min(lox, loy) >= -32768 && max(hix, hiy) <= 32767 &&
-          max(hix, hiy) - min(lox, loy) <= (1 << 15) - 1)) {
+    if (live && !(min(lox, loy) >= -32768 && max(hix, hiy) <= 32767 &&
+                  max(hix, hiy) - min(lox, loy) <= (1 << 15) - 1)) {
       clip_path = true;
-      continue;
+      live = false;
     }
     const int px0 = max((lox + bias + 15) >> 4, 0), px1 = min((hix + bias) >> 4, W - 1);
     const int py0 = max((loy + bias + 15) >> 4, row0), py1 = min((hiy + bias) >> 4, row0 + kTileRows - 1);
-    if (px0 > px1 || py0 > py1) continue;  // no sample of this band inside the bounding box
+    if (px0 > px1 || py0 > py1) live = false;  // no sample of this band inside the bounding box
     int d1x = p1x - p0x, d1y = p1y - p0y, d2x = p2x - p0x, d2y = p2y - p0y;
     int area = d1x * d2y - d1y * d2x;
-    if (area == 0) continue;
-    float z0 = A.z, z1 = B.z, z2 = C.z;
-    if (area < 0) {
-      int ti;
-      float tf;
-      ti = d1x; d1x = d2x; d2x = ti;
-      ti = d1y; d1y = d2y; d2y = ti;
-      ti = p1x; p1x = p2x; p2x = ti;
-      ti = p1y; p1y = p2y; p2y = ti;
-      tf = z1; z1 = z2; z2 = tf;
-      tf = rw1; rw1 = rw2; rw2 = tf;
-      area = -area;
-    }
-    const float zcoef = (float)(kDepthMax - kDepthMin) * 0.5f;
-    const float zbias = (float)(kDepthMax + kDepthMin) * 0.5f;
-    const float zv0 = fmaf(z0 * zcoef, rw0, zbias), zv1 = fmaf(z1 * zcoef, rw1, zbias),
-                zv2 = fmaf(z2 * zcoef, rw2, zbias);
-    unsigned pl[3];
-    setup_pleq(zv0, zv1, zv2, p0x + (W << 3) - 8, p0y + (H << 3) - 8, d1x, d1y, d2x, d2y,
-               1.0f / (float)area, pl);
-    const int e0x = d1x, e0y = d1y, e1x = d2x - d1x, e1y = d2y - d1y, e2x = -d2x, e2y = -d2y;
-    const long long adj0 = (e0y > 0 || (e0y == 0 && e0x <= 0)) ? 1 : 0;
-    const long long adj1 = (e1y > 0 || (e1y == 0 && e1x <= 0)) ? 1 : 0;
-    const long long adj2 = (e2y > 0 || (e2y == 0 && e2x <= 0)) ? 1 : 0;
-    const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - (unsigned)t);
-    for (int py = py0; py <= py1; ++py) {
-      const int sy = py * 16 - bias;
-      for (int px = px0; px <= px1; ++px) {
-        const int sx = px * 16 - bias;
-        const long long v0 = (long long)(p0x - sx) * e0y - (long long)(p0y - sy) * e0x - adj0;
-        const long long v1 = (long long)(p1x - sx) * e1y - (long long)(p1y - sy) * e1x - adj1;
-        const long long v2 = (long long)(p0x - sx) * e2y - (long long)(p0y - sy) * e2x - adj2;
-        if ((v0 | v1 | v2) < 0) continue;
-        const unsigned depth = pl[0] * (unsigned)px + pl[1] * (unsigned)py + pl[2];
-        if (depth > kDepthMax) continue;  // behind the cleared depth (FineRaster.inl:338)
-        atomicMin(&zbuf[(py - row0) * W + px], ((unsigned long long)depth << 32) | low);
+    if (area == 0) live = false;
+    if (live) {
+      float z0 = A.z, z1 = B.z, z2 = C.z;
+      if (area < 0) {
+        int ti;
+        float tf;
+        ti = d1x; d1x = d2x; d2x = ti;
+        ti = d1y; d1y = d2y; d2y = ti;
+        ti = p1x; p1x = p2x; p2x = ti;
+        ti = p1y; p1y = p2y; p2y = ti;
+        tf = z1; z1 = z2; z2 = tf;
+        tf = rw1; rw1 = rw2; rw2 = tf;
+        area = -area;
+      }
+      const float zcoef = (float)(kDepthMax - kDepthMin) * 0.5f;
+      const float zbias = (float)(kDepthMax + kDepthMin) * 0.5f;
+      const float zv0 = fmaf(z0 * zcoef, rw0, zbias), zv1 = fmaf(z1 * zcoef, rw1, zbias),
+                  zv2 = fmaf(z2 * zcoef, rw2, zbias);
+      unsigned pl[3];
+      setup_pleq(zv0, zv1, zv2, p0x + (W << 3) - 8, p0y + (H << 3) - 8, d1x, d1y, d2x, d2y,
+                 1.0f / (float)area, pl);
+      const int e0x = d1x, e0y = d1y, e1x = d2x - d1x, e1y = d2y - d1y, e2x = -d2x, e2y = -d2y;
+      const long long adj0 = (e0y > 0 || (e0y == 0 && e0x <= 0)) ? 1 : 0;
+      const long long adj1 = (e1y > 0 || (e1y == 0 && e1x <= 0)) ? 1 : 0;
+      const long long adj2 = (e2y > 0 || (e2y == 0 && e2x <= 0)) ? 1 : 0;
+      const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - (unsigned)t);
+      for (int py = py0; py <= py1; ++py) {
+        const int sy = py * 16 - bias;
+        for (int px = px0; px <= px1; ++px) {
+          const int sx = px * 16 - bias;
+          const long long v0 = (long long)(p0x - sx) * e0y - (long long)(p0y - sy) * e0x - adj0;
+          const long long v1 = (long long)(p1x - sx) * e1y - (long long)(p1y - sy) * e1x - adj1;
+          const long long v2 = (long long)(p0x - sx) * e2y - (long long)(p0y - sy) * e2x - adj2;
+          if ((v0 | v1 | v2) >= 0) {
+            const unsigned depth = pl[0] * (unsigned)px + pl[1] * (unsigned)py + pl[2];
+            // depth > kDepthMax would lie behind the cleared depth (FineRaster.inl:338)
+            if (depth <= kDepthMax) atomicMin(&zbuf[(py - row0) * W + px], ((unsigned long long)depth << 32) | low);
+          }
+        }
       }
     }
+    __syncwarp();
   }
   if (clip_path) atomicOr(status, kStatusClipPath);
   __syncthreads();

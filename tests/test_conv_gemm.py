@@ -12,6 +12,11 @@ from foundationpose_cpp_b200 import capi, layouts
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 2], ids=["cta", "pair"])
+def cluster(request):
+    return request.param
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -38,14 +43,14 @@ def _desc(**kw):
 
 @pytest.mark.parametrize("rows,k,cout,relu", [(1000, 512, 64, 1), (1000, 512, 128, 0), (777, 512, 256, 1),
                                               (4000, 512, 1536, 0), (128, 64, 512, 0), (50000, 512, 512, 1)])
-def test_linear(rows, k, cout, relu):
+def test_linear(rows, k, cout, relu, cluster):
     torch.manual_seed(0)
     x = _rand(rows, k)
     w = _rand(cout, k, scale=k ** -0.5)
     b = torch.randn(cout, device="cuda")
     out = torch.full((rows, cout), float("nan"), device="cuda", dtype=torch.float16)
     d = _desc(in_=_ptr(x), n_img=1, planes=1, in_h=1, in_w=rows, cin=k, out_h=1, out_w=rows, bw=128, bh=1, bn=1,
-              tap_kind=capi.TAPS_1X1, weight=_ptr(w), cout=cout, bias=_ptr(b), out=_ptr(out), relu=relu)
+              tap_kind=capi.TAPS_1X1, weight=_ptr(w), cout=cout, bias=_ptr(b), out=_ptr(out), relu=relu, cluster=cluster)
     capi.debug_conv_gemm(d)
     ref = x.float() @ w.float().t() + b
     if relu:
@@ -59,7 +64,7 @@ def test_linear(rows, k, cout, relu):
     (3, 20, 512, 512, (4, 4, 8), True, True),
     (2, 80, 64, 64, (16, 8, 1), False, False),
 ])
-def test_conv3x3_s1(n, hw, cin, cout, tile, residual, post):
+def test_conv3x3_s1(n, hw, cin, cout, tile, residual, post, cluster):
     torch.manual_seed(1)
     x = _rand(n, hw, hw, cin)
     w = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5)
@@ -70,7 +75,7 @@ def test_conv3x3_s1(n, hw, cin, cout, tile, residual, post):
     wp = layouts.pack_conv3x3(w)
     d = _desc(in_=_ptr(x), n_img=n, planes=1, in_h=hw, in_w=hw, cin=cin, out_h=hw, out_w=hw, bw=tile[0], bh=tile[1],
               bn=tile[2], tap_kind=capi.TAPS_3X3_S1, weight=_ptr(wp), cout=cout, bias=_ptr(b), residual=_ptr(res),
-              post_add=_ptr(pe), out=_ptr(out), relu=1)
+              post_add=_ptr(pe), out=_ptr(out), relu=1, cluster=cluster)
     capi.debug_conv_gemm(d)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
     if residual:
@@ -82,7 +87,7 @@ def test_conv3x3_s1(n, hw, cin, cout, tile, residual, post):
 
 
 @pytest.mark.parametrize("n,hw,cin,cout,tile", [(3, 80, 64, 128, (8, 8, 2)), (5, 40, 256, 512, (4, 4, 8))])
-def test_conv3x3_s2_phase_in(n, hw, cin, cout, tile):
+def test_conv3x3_s2_phase_in(n, hw, cin, cout, tile, cluster):
     torch.manual_seed(2)
     x = _rand(n, hw, hw, cin)
     xs = layouts.phase_split(x)
@@ -92,13 +97,13 @@ def test_conv3x3_s2_phase_in(n, hw, cin, cout, tile):
     out = torch.full((n, ho, ho, cout), float("nan"), device="cuda", dtype=torch.float16)
     d = _desc(in_=_ptr(xs), n_img=n, planes=4, in_h=ho, in_w=ho, cin=cin, out_h=ho, out_w=ho, bw=tile[0], bh=tile[1],
               bn=tile[2], tap_kind=capi.TAPS_3X3_S2_PHASE, weight=_ptr(layouts.pack_conv3x3(w)), cout=cout,
-              bias=_ptr(b), out=_ptr(out), relu=1)
+              bias=_ptr(b), out=_ptr(out), relu=1, cluster=cluster)
     capi.debug_conv_gemm(d)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=2, padding=1).permute(0, 2, 3, 1).relu()
     _check(out, ref, "conv3x3 s2")
 
 
-def test_stem7_and_phase_split_out():
+def test_stem7_and_phase_split_out(cluster):
     torch.manual_seed(3)
     n = 3
     x = _rand(n, 160, 160, 6)
@@ -110,13 +115,13 @@ def test_stem7_and_phase_split_out():
     d = _desc(in_=_ptr(buf), n_img=n, planes=2, in_h=80, in_w=80, cin=64, stride_w=32, stride_plane=pitch_b,
               stride_h=2 * pitch_b, stride_img=160 * pitch_b, out_h=80, out_w=80, bw=16, bh=8, bn=1,
               tap_kind=capi.TAPS_STEM7_ROWS, weight=_ptr(layouts.pack_stem7(w)), cout=64, bias=_ptr(b),
-              out=_ptr(out), relu=1, out_phase_split=1)
+              out=_ptr(out), relu=1, out_phase_split=1, cluster=cluster)
     capi.debug_conv_gemm(d)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=2, padding=3).permute(0, 2, 3, 1).relu()
     _check(layouts.phase_merge(out), ref, "stem 7x7 s2")
 
 
-def test_concat_halves():
+def test_concat_halves(cluster):
     """Images n >= img_mod land in the same pixel at a channel offset (a||b feature concat)."""
     torch.manual_seed(4)
     n, hw, c = 6, 40, 128
@@ -126,7 +131,7 @@ def test_concat_halves():
     out = torch.full((n // 2, hw, hw, 2 * c), float("nan"), device="cuda", dtype=torch.float16)
     d = _desc(in_=_ptr(x), n_img=n, planes=1, in_h=hw, in_w=hw, cin=c, out_h=hw, out_w=hw, bw=8, bh=8, bn=2,
               tap_kind=capi.TAPS_3X3_S1, weight=_ptr(layouts.pack_conv3x3(w)), cout=c, bias=_ptr(b), out=_ptr(out),
-              relu=1, out_ld=2 * c, img_mod=n // 2, half_coff=c)
+              relu=1, out_ld=2 * c, img_mod=n // 2, half_coff=c, cluster=cluster)
     capi.debug_conv_gemm(d)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1).relu()
     ref = torch.cat([ref[: n // 2], ref[n // 2:]], dim=-1)
