@@ -24,27 +24,38 @@ constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KB
 constexpr int kStageBytesPerWarp = 32 * 32 * 4;         // epilogue staging: 32 rows x 32 fp32 columns
 
-template <int BN>
+// MODE 0: independent CTAs.  MODE 1: CTA pairs, each CTA loads half of the weight tile and
+// multicasts it to both (halves the L2 reads of B; each SM still ingests A + B).  MODE 2: CTA pairs
+// issuing ONE tcgen05.mma.cta_group::2 of M = 256: each SM holds (and ingests) its 128 activation
+// rows and only HALF of the weight tile, which is what lifts the shared-memory fill-rate bound of the
+// narrower tiles.
+template <int BN, int MODE>
 struct Cfg {
-  static constexpr int kBBytes = BN * kGemmBlockK * 2;
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kCS = MODE == 0 ? 1 : 2;
+  static constexpr int kBBytes = (BN * kGemmBlockK * 2) / (MODE == 2 ? 2 : 1);  // per CTA and k-block
+  // k-blocks per pipeline stage: the producer / MMA warps synchronise once per stage, and that
+  // hand-shake (try_wait + fence + elect + commit, ~500 cycles of warp time) has to be covered by the
+  // tensor-core time of the stage: 4 MMAs of N=256 cover it, 4 MMAs of N<=128 do not.
+  static constexpr int kKS = BN == 256 ? 1 : 2;
+  static constexpr int kStageBytes = kKS * (kABytes + kBBytes);
+  static constexpr int kStages = (192 * 1024) / kStageBytes > 10 ? 10 : (192 * 1024) / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr size_t kSmem = 1024 /*alignment slack*/ + size_t(kStages) * (kABytes + kBBytes) +
+  static constexpr size_t kSmem = 1024 /*alignment slack*/ + size_t(kStages) * kStageBytes +
                                   8 * kStageBytesPerWarp /*epilogue staging*/ + 256 /*barriers*/;
 };
 
-// CS = cluster size: the CS CTAs of a cluster work on CS consecutive M tiles of the same N tile in
-// lock step; each loads 1/CS of the weight tile and multicasts it to all, so the L2 -> SM traffic
-// per CTA and k-block drops from A + B to A + B/CS.
-template <int BN, int CS>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MODE>;
+  constexpr int CS = C::kCS;
+  constexpr bool kPairMma = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + C::kStages * kABytes;
-  const uint32_t stage_base = b_base + C::kStages * C::kBBytes;
+  constexpr int KS = C::kKS;
+  const uint32_t a_base = smem_base;                                // [stage][sub] activation tiles
+  const uint32_t b_base = smem_base + C::kStages * KS * kABytes;    // [stage][sub] weight tiles
+  const uint32_t stage_base = b_base + C::kStages * KS * C::kBBytes;
   const uint32_t bar_base = stage_base + 8 * kStageBytesPerWarp;
   // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -60,20 +71,28 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), CS);  // one tcgen05.commit arrival from every CTA of the cluster
+      // MODE 2: the leader's full barrier takes one expect_tx arrival from each CTA's producer
+      ptx::mbar_init(full_bar(s), kPairMma ? 2 : 1);
+      // MODE 1: one tcgen05.commit arrival from every CTA; MODE 2: one multicast commit by the leader
+      ptx::mbar_init(empty_bar(s), MODE == 1 ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      ptx::mbar_init(tempty_bar(s), 256);
+      // one arrival per epilogue warp (MODE 2: of both CTAs, on the leader's barrier)
+      ptx::mbar_init(tempty_bar(s), kPairMma ? 16 : 8);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tm_a);
     ptx::prefetch_tensormap(&p.tm_b);
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, C::kTmemCols);
-    ptx::tmem_relinquish();
+    if (kPairMma) {
+      ptx::tmem_alloc_pair(tmem_slot, C::kTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -91,7 +110,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr uint16_t kAllCtas = (uint16_t)((1u << CS) - 1u);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -100,33 +119,43 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int x0 = (mt % p.tiles_x) * p.bw;
         const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
         const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
-        int kb = 0;
-        for (int t = 0; t < p.num_taps; ++t) {
-          const int cx = x0 + p.tap_dx[t];
-          const int cy = y0 + p.tap_dy[t];
-          const int cp = p.tap_plane[t];
-          for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-            ptx::mbar_expect_tx(full_bar(stage), kABytes + C::kBBytes);
-            ptx::tma_load_5d(a_base + stage * kABytes, &p.tm_a, full_bar(stage), cb * kGemmBlockK,
-                             cx, cy, cp, n0);
-            if (CS == 1) {
-              ptx::tma_load_2d(b_base + stage * C::kBBytes, &p.tm_b, full_bar(stage), kb * kGemmBlockK, nt * BN);
-            } else {
-              ptx::tma_load_2d_mcast(b_base + stage * C::kBBytes + crank * (C::kBBytes / CS), &p.tm_b,
-                                     full_bar(stage), kb * kGemmBlockK, nt * BN + crank * (BN / CS), kAllCtas);
+        for (int kb0 = 0; kb0 < kblocks; kb0 += KS) {
+          const int nsub = min(KS, kblocks - kb0);
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (ptx::elect_one()) {
+            const uint32_t bytes = nsub * (kABytes + C::kBBytes);
+            // MODE 2: both CTAs report their bytes to (and land their loads on) the LEADER's barrier
+            const uint32_t bar = kPairMma ? ptx::mapa_rank(full_bar(stage), 0) : full_bar(stage);
+            if (kPairMma) ptx::mbar_expect_tx_cluster(bar, bytes);
+            else ptx::mbar_expect_tx(bar, bytes);
+            for (int sub = 0; sub < nsub; ++sub) {
+              const int kb = kb0 + sub;
+              const int t = kb / p.cblocks, cb = kb - t * p.cblocks;
+              const int cx = x0 + p.tap_dx[t], cy = y0 + p.tap_dy[t], cp = p.tap_plane[t];
+              const uint32_t a_dst = a_base + (stage * KS + sub) * kABytes;
+              const uint32_t b_dst = b_base + (stage * KS + sub) * C::kBBytes;
+              if (kPairMma) {
+                ptx::tma_load_5d_pair(a_dst, &p.tm_a, bar, cb * kGemmBlockK, cx, cy, cp, n0);
+                ptx::tma_load_2d_pair(b_dst, &p.tm_b, bar, kb * kGemmBlockK, nt * BN + crank * (BN / 2));
+              } else {
+                ptx::tma_load_5d(a_dst, &p.tm_a, bar, cb * kGemmBlockK, cx, cy, cp, n0);
+                if (MODE == 0) ptx::tma_load_2d(b_dst, &p.tm_b, bar, kb * kGemmBlockK, nt * BN);
+                else ptx::tma_load_2d_mcast(b_dst + crank * (C::kBBytes / 2), &p.tm_b, bar, kb * kGemmBlockK,
+                                            nt * BN + crank * (BN / 2), kAllCtas);
+              }
             }
-            if (++stage == C::kStages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          }
+          __syncwarp();
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(kGemmBlockM, BN);
+    if (!kPairMma || crank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kPairMma ? 256 : kGemmBlockM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -136,25 +165,37 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb0 = 0; kb0 < kblocks; kb0 += KS) {
+          const int nsub = min(KS, kblocks - kb0);
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
-          const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_base + stage * kABytes);
-          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(b_base + stage * C::kBBytes);
+          if (ptx::elect_one()) {
+            for (int sub = 0; sub < nsub; ++sub) {
+              const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_base + (stage * KS + sub) * kABytes);
+              const uint64_t bdesc = ptx::make_sw128_kmajor_desc(b_base + (stage * KS + sub) * C::kBBytes);
 #pragma unroll
-          for (int k = 0; k < kGemmBlockK / 16; ++k) {
-            // advancing 16 fp16 along K inside the 128-byte swizzle row = +32 B = +2 in the
-            // descriptor's 16-byte address units
-            ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                // advancing 16 fp16 along K inside the 128-byte swizzle row = +32 B = +2 in the
+                // descriptor's 16-byte address units
+                const uint32_t accum = (kb0 | sub | k) != 0;
+                if (kPairMma) ptx::umma_f16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
+                else ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
+              }
+            }
+            if (MODE == 0) ptx::umma_commit(empty_bar(stage));
+            else if (MODE == 1) ptx::umma_commit_mcast(empty_bar(stage), kAllCtas);
+            else ptx::umma_commit_pair_mcast(empty_bar(stage), kAllCtas);
+            if (kb0 + KS >= kblocks) {
+              if (kPairMma) ptx::umma_commit_pair_mcast(tfull_bar(acc), kAllCtas);
+              else ptx::umma_commit(tfull_bar(acc));
+            }
           }
-          if (CS == 1) ptx::umma_commit(empty_bar(stage));
-          else ptx::umma_commit_mcast(empty_bar(stage), kAllCtas);
+          __syncwarp();
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        ptx::umma_commit(tfull_bar(acc));
       }
     }
   } else {
@@ -278,7 +319,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      if (lane == 0) {
+        if (kPairMma) ptx::mbar_arrive_cluster(ptx::mapa_rank(tempty_bar(acc), 0));
+        else ptx::mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
@@ -287,7 +332,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (CS > 1) ptx::cluster_sync();  // no CTA exits while a peer may still signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    if (kPairMma) ptx::tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -311,12 +357,15 @@ const char* conv_gemm_init() {
   auto set_attr = [&](auto kernel, size_t smem) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   };
-  set_attr(conv_gemm_kernel<64, 1>, Cfg<64>::kSmem);
-  set_attr(conv_gemm_kernel<128, 1>, Cfg<128>::kSmem);
-  set_attr(conv_gemm_kernel<256, 1>, Cfg<256>::kSmem);
-  set_attr(conv_gemm_kernel<64, 2>, Cfg<64>::kSmem);
-  set_attr(conv_gemm_kernel<128, 2>, Cfg<128>::kSmem);
-  set_attr(conv_gemm_kernel<256, 2>, Cfg<256>::kSmem);
+  set_attr(conv_gemm_kernel<64, 0>, Cfg<64, 0>::kSmem);
+  set_attr(conv_gemm_kernel<128, 0>, Cfg<128, 0>::kSmem);
+  set_attr(conv_gemm_kernel<256, 0>, Cfg<256, 0>::kSmem);
+  set_attr(conv_gemm_kernel<64, 1>, Cfg<64, 1>::kSmem);
+  set_attr(conv_gemm_kernel<128, 1>, Cfg<128, 1>::kSmem);
+  set_attr(conv_gemm_kernel<256, 1>, Cfg<256, 1>::kSmem);
+  set_attr(conv_gemm_kernel<64, 2>, Cfg<64, 2>::kSmem);
+  set_attr(conv_gemm_kernel<128, 2>, Cfg<128, 2>::kSmem);
+  set_attr(conv_gemm_kernel<256, 2>, Cfg<256, 2>::kSmem);
   if (e != cudaSuccess) return "cudaFuncSetAttribute(max dynamic smem) failed (not an sm_100a device?)";
   int dev = 0;
   cudaGetDevice(&dev);
@@ -375,14 +424,13 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   if (out_ld % 8 || d.half_coff % 8) return "conv_gemm: output leading dims must be multiples of 8";
   if (d.out_phase_split && ((d.out_h | d.out_w) & 1)) return "conv_gemm: phase-split needs even H, W";
 
-  // cluster size: pairs of CTAs share the weight tile by multicast when there is enough work
+  // pairing mode (see Cfg): 0 = single CTAs, 1 = pair + weight multicast, 2 = pair + cta_group::2 MMA
   const long long m_tiles_all = (long long)((d.out_w + d.bw - 1) / d.bw) * ((d.out_h + d.bh - 1) / d.bh) *
                                 ((d.n_img + d.bn - 1) / d.bn);
-  // (measured on B200: multicast pays for the 256-wide tiles only; narrower tiles are bound by the
-  // SM's shared-memory fill rate, which multicast does not reduce)
-  int cluster = d.cluster > 0 ? d.cluster : ((m_tiles_all >= 2 * g_num_sms && d.cout % 256 == 0) ? 2 : 1);
-  if (const char* env = getenv("FPB_GEMM_CLUSTER")) cluster = atoi(env) == 1 ? 1 : 2;
-  if (cluster != 1 && cluster != 2) return "conv_gemm: cluster must be 1 or 2";
+  int mode = d.cluster > 0 ? d.cluster - 1 : (m_tiles_all >= 2 * g_num_sms ? 2 : 0);
+  if (const char* env = getenv("FPB_GEMM_MODE")) mode = atoi(env);
+  if (mode < 0 || mode > 2) return "conv_gemm: pairing mode must be 0, 1 or 2";
+  const int cluster = mode == 0 ? 1 : 2;
   ConvGemmParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   {
@@ -448,20 +496,27 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   p.out_ld = out_ld;
   p.img_mod = d.img_mod ? d.img_mod : d.n_img;
   p.half_coff = d.half_coff;
+  if (const char* env = getenv("FPB_GEMM_DEBUG")) p.debug = atoi(env);
 
   plan->block_n = bn_tile;
   plan->cluster = cluster;
+  plan->mode = mode;
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_img;
   const long long work = ((m_tiles + cluster - 1) / cluster) * p.n_tiles;  // per cluster
   const int cap = (d.max_ctas > 0 ? d.max_ctas : g_num_sms) / cluster;
   plan->grid = (int)(work < cap ? work : cap) * cluster;
-  plan->smem = bn_tile == 256 ? Cfg<256>::kSmem : (bn_tile == 128 ? Cfg<128>::kSmem : Cfg<64>::kSmem);
+  {
+    const size_t sm[3][3] = {{Cfg<64, 0>::kSmem, Cfg<64, 1>::kSmem, Cfg<64, 2>::kSmem},
+                             {Cfg<128, 0>::kSmem, Cfg<128, 1>::kSmem, Cfg<128, 2>::kSmem},
+                             {Cfg<256, 0>::kSmem, Cfg<256, 1>::kSmem, Cfg<256, 2>::kSmem}};
+    plan->smem = sm[bn_tile == 256 ? 2 : (bn_tile == 128 ? 1 : 0)][mode];
+  }
   plan->flops = 2.0 * d.n_img * d.out_h * d.out_w * (double)d.cout * d.num_taps * d.cin;
   return nullptr;
 }
 
 namespace {
-template <int BN, int CS>
+template <int BN, int MODE>
 cudaError_t launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan.grid);
@@ -470,22 +525,29 @@ cudaError_t launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.x = Cfg<BN, MODE>::kCS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CS>, plan.p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, MODE>, plan.p);
+}
+template <int BN>
+cudaError_t launch_bn(const ConvGemmPlan& plan, cudaStream_t stream) {
+  switch (plan.mode) {
+    case 2: return launch_one<BN, 2>(plan, stream);
+    case 1: return launch_one<BN, 1>(plan, stream);
+    default: return launch_one<BN, 0>(plan, stream);
+  }
 }
 }  // namespace
 
 cudaError_t launch_conv_gemm(const ConvGemmPlan& plan, cudaStream_t stream) {
   if (plan.grid <= 0) return cudaSuccess;
-  const bool pair = plan.cluster == 2;
   switch (plan.block_n) {
-    case 256: return pair ? launch_one<256, 2>(plan, stream) : launch_one<256, 1>(plan, stream);
-    case 128: return pair ? launch_one<128, 2>(plan, stream) : launch_one<128, 1>(plan, stream);
-    default: return pair ? launch_one<64, 2>(plan, stream) : launch_one<64, 1>(plan, stream);
+    case 256: return launch_bn<256>(plan, stream);
+    case 128: return launch_bn<128>(plan, stream);
+    default: return launch_bn<64>(plan, stream);
   }
 }
 

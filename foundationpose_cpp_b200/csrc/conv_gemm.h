@@ -46,6 +46,7 @@ struct ConvGemmParams {
   int out_ld;           // channels per pixel of the destination tensor
   int img_mod;          // images per half: image n is written as image n % img_mod ...
   int half_coff;        // ... at channel offset (n / img_mod) * half_coff
+  int debug;            // timing experiments only (FPB_GEMM_DEBUG): 1 alternate accumulators, 2 skip B loads, 4 skip A loads
 };
 
 // Host-side description of a layer; build_conv_gemm() turns it into launchable params.
@@ -72,13 +73,15 @@ struct ConvGemmDesc {
   int img_mod = 0;  // 0 -> n_img
   int half_coff = 0;
   int max_ctas = 0;  // 0 -> number of SMs
-  int cluster = 0;   // CTAs sharing a weight tile by TMA multicast: 1 or 2 (0 -> automatic)
+  int cluster = 0;   // 0 -> automatic; 1 = single CTAs; 2 = CTA pairs + weight multicast;
+                     // 3 = CTA pairs issuing tcgen05.mma.cta_group::2 (M = 256)
 };
 
 struct ConvGemmPlan {
   ConvGemmParams p;
   int block_n = 0;
-  int cluster = 1;
+  int cluster = 1;  // CTAs per cluster
+  int mode = 0;     // 0 single, 1 pair + multicast, 2 pair + cta_group::2
   int grid = 0;
   size_t smem = 0;
   double flops = 0;  // 2*M*N*K over valid rows

@@ -155,7 +155,7 @@ typedef struct {
   const float* post_add;
   void* out; /* f16 */
   int relu, out_phase_split, out_ld, img_mod, half_coff, max_ctas;
-  int cluster; /* 0 = automatic, 1 = single CTAs, 2 = CTA pairs sharing the weight tile by TMA multicast */
+  int cluster; /* 0 = automatic, 1 = single CTAs, 2 = CTA pairs + weight multicast, 3 = CTA pairs + cta_group::2 MMA */
 } fpb200_conv_desc;
 /* Runs the tcgen05 implicit-GEMM kernel once (+ `repeat` timed launches; avg ms -> *ms_out). */
 int fpb200_debug_conv_gemm(const fpb200_conv_desc* desc, int repeat, float* ms_out);
