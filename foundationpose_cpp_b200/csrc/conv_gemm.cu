@@ -108,6 +108,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int cluster_id = blockIdx.x / CS;
   const int num_clusters = gridDim.x / CS;
   constexpr uint16_t kAllCtas = (uint16_t)((1u << CS) - 1u);
+  constexpr int n_stages = C::kStages;
 
   if (warp == 0) {
     {
@@ -146,7 +147,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
           }
           __syncwarp();
-          if (++stage == C::kStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -191,7 +192,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
           }
           __syncwarp();
-          if (++stage == C::kStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -264,21 +265,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      // The TMEM read of chunk c+1 is issued as soon as chunk c has been staged, so its latency
+      // overlaps the arithmetic and stores of chunk c.
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c_first, r);
 #pragma unroll 1
       for (int c0 = c_first; c0 < BN; c0 += 64) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr + c0));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bptr + c0 + 4));
-        {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(taddr + c0, r);
-          ptx::tmem_ld_wait();
+        ptx::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            ptx::st_shared_v4(wr_base + ((c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-        }
+        for (int c = 0; c < 8; ++c)
+          ptx::st_shared_v4(wr_base + ((c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
         __syncwarp();
         uint4 res_nxt[4];
-        if (c0 + 64 < BN) fetch_residual(res_nxt, c0 + 64);
+        if (c0 + 64 < BN) {
+          ptx::tmem_ld_32x32b_x32(taddr + c0 + 64, r);
+          fetch_residual(res_nxt, c0 + 64);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t rd = stg + (i * 8 + sub) * 128;
@@ -318,6 +322,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int i = 0; i < 4; ++i) res_cur[i] = res_nxt[i];
         }
       }
+      ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -496,7 +501,6 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   p.out_ld = out_ld;
   p.img_mod = d.img_mod ? d.img_mod : d.n_img;
   p.half_coff = d.half_coff;
-  if (const char* env = getenv("FPB_GEMM_DEBUG")) p.debug = atoi(env);
 
   plan->block_n = bn_tile;
   plan->cluster = cluster;

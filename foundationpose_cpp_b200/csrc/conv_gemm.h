@@ -46,7 +46,6 @@ struct ConvGemmParams {
   int out_ld;           // channels per pixel of the destination tensor
   int img_mod;          // images per half: image n is written as image n % img_mod ...
   int half_coff;        // ... at channel offset (n / img_mod) * half_coff
-  int debug;            // timing experiments only (FPB_GEMM_DEBUG): 1 alternate accumulators, 2 skip B loads, 4 skip A loads
 };
 
 // Host-side description of a layer; build_conv_gemm() turns it into launchable params.

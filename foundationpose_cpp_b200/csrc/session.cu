@@ -187,11 +187,19 @@ struct fpb200_session {
   int launches = 0;        // since the last Register/Track/upload
   long long launches_total = 0;
   float crop_ratio_last = 0.f;
+  bool in_graph = false;      // capturing or about to replay: no event marks
+  struct GraphEntry {
+    bool seen = false;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+  };
+  std::map<std::string, GraphEntry> graphs;  // Register / Track launch sequences, keyed by their static parameters
   bool async_stages = false;  // stage calls return without synchronising the stream
   bool mask_resident = false;
   bool profile_gemm = false;
 
   ~fpb200_session() {
+    for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     if (host_result) cudaFreeHost(host_result);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -209,6 +217,7 @@ struct fpb200_session {
     if (!async_stages) FPB_CUDA(cudaStreamSynchronize(stream));
   }
   void mark(int i) {
+    if (in_graph) return;  // stage timings are only taken on the eager path
     FPB_CUDA(cudaEventRecord(ev[i], stream));
     ev_valid[i] = true;
   }
@@ -251,19 +260,25 @@ void do_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h,
   s->mark(0);
   FPB_CUDA(cudaMemcpyAsync(s->rgb.p, rgb, (size_t)h * w * 3, cudaMemcpyHostToDevice, s->stream));
   FPB_CUDA(cudaMemcpyAsync(s->depth.p, depth, sizeof(float) * (size_t)h * w, cudaMemcpyHostToDevice, s->stream));
-  launch_depth_to_xyz(s->depth.p, s->xyz.p, h, w, s->intr, s->stream);
-  s->count_launches(1);
   s->uploaded = true;
+}
+
+void do_xyz(fpb200_session* s) {
+  launch_depth_to_xyz(s->depth.p, s->xyz.p, s->img_h, s->img_w, s->intr, s->stream);
+  s->count_launches(1);
   s->mark(1);
 }
 
-void do_sample(fpb200_session* s, const uint8_t* mask, MeshEntry* mesh) {
-  const int h = s->img_h, w = s->img_w;
+void do_mask_copy(fpb200_session* s, const uint8_t* mask) {
   if (mask) {
-    FPB_CUDA(cudaMemcpyAsync(s->mask.p, mask, (size_t)h * w, cudaMemcpyHostToDevice, s->stream));
+    FPB_CUDA(cudaMemcpyAsync(s->mask.p, mask, (size_t)s->img_h * s->img_w, cudaMemcpyHostToDevice, s->stream));
     s->mask_resident = true;
   }
   FPB_REQUIRE(s->mask_resident, "mask must not be null (no mask is resident on the device yet)");
+}
+
+void do_sample(fpb200_session* s, MeshEntry* mesh) {
+  const int h = s->img_h, w = s->img_w;
   launch_depth_filters(s->depth.p, s->eroded.p, s->filtered.p, h, w, s->stream);
   launch_guess_translation(s->filtered.p, s->mask.p, h, w, s->intr, s->center.p, s->status.p, s->sampler_scratch.p,
                            s->stream);
@@ -382,6 +397,53 @@ int finish_and_read(fpb200_session* s, float out_pose[16], int* best_index) {
   return wait_result(s, out_pose, best_index);
 }
 
+// Runs `body` (a fixed launch sequence on s->stream).  The first call with a given key runs it
+// eagerly (this also builds every lazily created plan), the second call captures it into a CUDA
+// graph, later calls replay the graph: one cudaGraphLaunch instead of ~70 kernel launches.
+template <typename F>
+void run_maybe_graphed(fpb200_session* s, const std::string& key, F&& body) {
+  if (!s->opt.use_cuda_graph || s->profile_gemm) {
+    body();
+    return;
+  }
+  fpb200_session::GraphEntry& g = s->graphs[key];
+  if (g.exec) {
+    FPB_CUDA(cudaGraphLaunch(g.exec, s->stream));
+    s->count_launches(g.launches);
+    return;
+  }
+  if (!g.seen) {
+    g.seen = true;
+    body();
+    return;
+  }
+  const int before = s->launches;
+  s->in_graph = true;
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
+  if (e == cudaSuccess) {
+    try {
+      body();
+    } catch (...) {
+      cudaStreamEndCapture(s->stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      s->in_graph = false;
+      throw;
+    }
+    e = cudaStreamEndCapture(s->stream, &graph);
+  }
+  s->in_graph = false;
+  if (e != cudaSuccess || !graph) throw CudaError(std::string("CUDA graph capture failed: ") + cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    g.exec = nullptr;
+    throw CudaError(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(e));
+  }
+  g.launches = s->launches - before;
+  FPB_CUDA(cudaGraphLaunch(g.exec, s->stream));
+}
+
 void reset_call(fpb200_session* s) {
   s->launches = 0;
   for (auto& v : s->ev_valid) v = false;
@@ -398,7 +460,7 @@ void fpb200_default_options(fpb200_options* o) {
   o->max_hyps = kGridPoses;
   o->shard_rank = 0;
   o->shard_world = 1;
-  o->use_cuda_graph = 0;
+  o->use_cuda_graph = 1;
 }
 
 int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], int max_h, int max_w,
@@ -522,14 +584,25 @@ int fpb200_register(fpb200_session* s, const uint8_t* rgb, const float* depth, c
     FPB_REQUIRE(refine_itr >= 0, "refine_itr must be >= 0");
     reset_call(s);
     do_upload(s, rgb, depth, h, w);
-    do_sample(s, mask, mesh);
-    for (int i = 0; i < refine_itr; ++i) do_refine_step(s);
-    s->mark(4);
-    do_score_features(s);
-    s->mark(5);
-    do_score_finish(s);
-    s->mark(6);
-    return finish_and_read(s, out_pose, nullptr);
+    do_mask_copy(s, mask);
+    // host-side state of the call (not part of the captured launch sequence)
+    s->cur_mesh = mesh;
+    s->set_shard(std::min(kGridPoses, s->opt.max_hyps));
+    char key[160];
+    snprintf(key, sizeof(key), "register:%d:%dx%d:%p", refine_itr, h, w, (void*)mesh);
+    run_maybe_graphed(s, key, [&]() {
+      do_xyz(s);
+      do_sample(s, mesh);
+      for (int i = 0; i < refine_itr; ++i) do_refine_step(s);
+      s->mark(4);
+      do_score_features(s);
+      s->mark(5);
+      do_score_finish(s);
+      s->mark(6);
+      enqueue_result_read(s);
+    });
+    s->features_ready = true;
+    return wait_result(s, out_pose, nullptr);
   });
 }
 
@@ -545,10 +618,15 @@ int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int 
     FPB_CUDA(cudaMemcpyAsync(s->poses.p, hyp_pose, sizeof(float) * 16, cudaMemcpyHostToDevice, s->stream));
     s->cur_mesh = mesh;
     s->n_hyp = 1; s->lo = 0; s->hi = 1; s->shard_cap = 1; s->features_ready = false;
-    s->mark(2);
-    for (int i = 0; i < refine_itr; ++i) do_refine_step(s);
-    s->mark(4);
-    FPB_CUDA(cudaMemcpyAsync(s->host_result->pose, s->poses.p, sizeof(float) * 16, cudaMemcpyDeviceToHost, s->stream));
+    char key[160];
+    snprintf(key, sizeof(key), "track:%d:%dx%d:%p", refine_itr, h, w, (void*)mesh);
+    run_maybe_graphed(s, key, [&]() {
+      do_xyz(s);
+      s->mark(2);
+      for (int i = 0; i < refine_itr; ++i) do_refine_step(s);
+      s->mark(4);
+      FPB_CUDA(cudaMemcpyAsync(s->host_result->pose, s->poses.p, sizeof(float) * 16, cudaMemcpyDeviceToHost, s->stream));
+    });
     FPB_CUDA(cudaStreamSynchronize(s->stream));
     memcpy(out_pose, s->host_result->pose, sizeof(float) * 16);
     return FPB200_OK;
@@ -560,6 +638,7 @@ int fpb200_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int
     FPB_REQUIRE(s, "null session");
     reset_call(s);
     do_upload(s, rgb, depth, h, w);
+    do_xyz(s);
     return FPB200_OK;
   });
 }
@@ -570,7 +649,8 @@ int fpb200_sample_hypotheses(fpb200_session* s, const uint8_t* mask, const char*
     if (!s->uploaded) return fail(FPB200_ERR_STATE, "fpb200_upload must be called first");
     MeshEntry* mesh = s->find_mesh(target_name);
     FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
-    do_sample(s, mask, mesh);
+    do_mask_copy(s, mask);
+    do_sample(s, mesh);
     if (s->async_stages) return FPB200_OK;  // status is checked by fpb200_wait
     FPB_CUDA(cudaMemcpyAsync(&s->host_result->status, s->status.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     FPB_CUDA(cudaStreamSynchronize(s->stream));
@@ -750,6 +830,7 @@ int fpb200_wait(fpb200_session* s, int* best_index, float out_pose[16]) {
 int fpb200_set_gemm_profile(fpb200_session* s, int on) {
   return guard([&]() -> int {
     FPB_REQUIRE(s, "null session");
+    s->profile_gemm = on != 0;
     s->refiner->set_profile(on != 0);
     s->scorer->set_profile(on != 0);
     return FPB200_OK;

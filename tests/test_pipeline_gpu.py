@@ -175,3 +175,18 @@ def test_register_and_track_end_to_end(env):
     assert not ok4
     ok5, _ = m.Register(env["rgb"][:100], env["depth"], env["mask"], "mustard_proxy")
     assert not ok5
+
+
+def test_cuda_graph_replay_matches_eager(env):
+    """Register / Track run eagerly on the first call, are captured into a CUDA graph on the second and
+    replayed afterwards: all three must return the same pose bit for bit."""
+    m = env["model"]
+    poses = [m.Register(env["rgb"], env["depth"], env["mask"], "mustard_proxy", refine_itr=2)[1] for _ in range(4)]
+    for p in poses[1:]:
+        assert np.array_equal(p, poses[0])
+    tr = [m.Track(env["rgb"], env["depth"], poses[0], "mustard_proxy", refine_itr=1)[1] for _ in range(4)]
+    for p in tr[1:]:
+        assert np.array_equal(p, tr[0])
+    # a different image size or refine count is a different graph
+    ok, p2 = m.Register(env["rgb"], env["depth"], env["mask"], "mustard_proxy", refine_itr=1)
+    assert ok and np.isfinite(p2).all()
