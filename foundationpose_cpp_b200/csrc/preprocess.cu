@@ -643,7 +643,30 @@ __global__ void warp_kernel(const uint8_t* __restrict__ rgb, const float* __rest
   *reinterpret_cast<uint4*>(img + ((long long)y * kStemPitch + kStemPad + x) * kPackC) = pk;
 }
 
+__global__ void repack_f32_kernel(const float* __restrict__ blob, long long npix, __half* __restrict__ packed,
+                                  int img0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const long long img = i / (kCrop * kCrop);
+  const int r = (int)(i - img * (kCrop * kCrop));
+  const int y = r / kCrop, x = r - y * kCrop;
+  const float* src = blob + i * 6;
+  uint4 pk;
+  __half2* hp = reinterpret_cast<__half2*>(&pk);
+  hp[0] = __floats2half2_rn(src[0], src[1]);
+  hp[1] = __floats2half2_rn(src[2], src[3]);
+  hp[2] = __floats2half2_rn(src[4], src[5]);
+  hp[3] = __floats2half2_rn(0.f, 0.f);
+  *reinterpret_cast<uint4*>(packed + (img0 + img) * kPackImageElems + ((long long)y * kStemPitch + kStemPad + x) * kPackC) = pk;
+}
+
 }  // namespace
+
+void launch_repack_f32(const float* blob, int n, __half* packed, int img0, cudaStream_t s) {
+  if (n <= 0) return;
+  const long long npix = (long long)n * kCrop * kCrop;
+  repack_f32_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(blob, npix, packed, img0);
+}
 
 const char* preprocess_init() {
   cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

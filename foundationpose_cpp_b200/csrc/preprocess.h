@@ -69,6 +69,9 @@ void launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vc
 // Crop/warp the observed rgb + xyz, normalise, pack into packed image `img0 + i`.
 void launch_warp(const uint8_t* rgb, const float* xyz, int h, int w, const PoseAux* aux, int n,
                  float diameter, __half* packed, int img0, cudaStream_t s);
+// The reference's engine blobs (f32 NHWC [n,160,160,6], foundationpose.cpp:349-354) -> packed fp16
+// network input images img0 .. img0+n-1.
+void launch_repack_f32(const float* blob, int n, __half* packed, int img0, cudaStream_t s);
 const char* preprocess_init();  // kernel attributes; nullptr on success
 
 }  // namespace fpb

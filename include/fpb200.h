@@ -135,6 +135,21 @@ int fpb200_wait(fpb200_session* s, int* best_index, float out_pose[16]);
 int fpb200_set_gemm_profile(fpb200_session* s, int on);
 int fpb200_gemm_profile(fpb200_session* s, double* ms, double* flops, long long* launches);
 
+/* ---- inference-core boundary: the refine / score networks alone, behind the plugin interface the
+ * reference uses for its TensorRT engines.  Replaces CreateTrtInferCore + BaseInferCore::SyncInfer
+ * (edt/inference_core/trt_core/include/trt_core/trt_core.h:26-30,
+ *  edt/deploy_core/include/deploy_core/base_infer_core.h:179-237) with DEVICE-located blobs in the
+ * reference's own layout: render_input / transf_input f32 NHWC [n,160,160,6]
+ * (fp/src/foundationpose.cpp:78-83,349-354) -> trans [n,3] + rot [n,3], or scores [n]. ---- */
+typedef struct fpb200_infer_core fpb200_infer_core;
+int fpb200_infer_create(const char* weights, int kind /*0 refiner, 1 scorer*/, int max_batch, int device,
+                        fpb200_infer_core** out);
+void fpb200_infer_destroy(fpb200_infer_core* core);
+int fpb200_infer_refiner(fpb200_infer_core* core, const float* render_input, const float* transf_input, int n,
+                         float* trans, float* rot);
+int fpb200_infer_scorer(fpb200_infer_core* core, const float* render_input, const float* transf_input, int n,
+                        float* scores);
+
 /* ---- kernel-level debug entry points (DEVICE pointers) ---- */
 enum {
   FPB200_TAPS_1X1 = 0,

@@ -138,3 +138,31 @@ def test_allgather_layout_gloo_world2():
                            capture_output=True, text=True, timeout=240)
         assert r.returncode == 0, r.stdout + r.stderr
         assert r.stdout.count("ok") == 2
+
+
+def test_obj_mesh_loader_roundtrip(tmp_path):
+    from foundationpose_cpp_b200 import mesh_loader, synth
+    m = synth.uv_ellipsoid("obj", slices=16, stacks=9, tex_size=32, seed=3)
+    p = str(tmp_path / "m.obj")
+    mesh_loader.save_obj(p, m.vertices, m.normals, m.texcoords, m.faces, m.texture)
+    ld = mesh_loader.CreateAssimpMeshLoader("obj", p)
+    assert ld.GetName() == "obj"
+    # vertices are re-indexed in order of first use (like assimp's JoinIdenticalVertices): compare per corner
+    f2 = ld.GetMeshTriangleFaces()
+    assert f2.shape == m.faces.shape and ld.GetMeshNumVertices() <= len(m.vertices)
+    np.testing.assert_allclose(ld.GetMeshVertices()[f2], m.vertices[m.faces], atol=1e-6)
+    np.testing.assert_allclose(ld.GetMeshVertexNormals()[f2], m.normals[m.faces], atol=1e-5)
+    np.testing.assert_allclose(ld.GetMeshTextureCoords()[f2], m.texcoords[m.faces], atol=1e-6)
+    assert np.array_equal(ld.GetTextureMap(), m.texture)
+    np.testing.assert_allclose(ld.GetMeshModelCenter(), m.center, atol=1e-6)
+    assert abs(ld.GetMeshDiameter() - m.diameter) < 1e-3  # max pairwise distance of the tessellated ellipsoid
+    # quads are fan-triangulated, shared corners are joined, missing texture -> 2x2 grey like the reference
+    q = str(tmp_path / "quad.obj")
+    open(q, "w").write("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nf 1/1 2/2 3/3 4/4\n")
+    v, n, t, f, tex = mesh_loader.load_obj(q)
+    assert f.tolist() == [[0, 1, 2], [0, 2, 3]] and v.shape == (4, 3)
+    np.testing.assert_allclose(n, [[0, 0, 1]] * 4)
+    assert tex.shape == (2, 2, 3) and np.all(tex == 100)
+    open(q, "w").write("v 0 0 0\nv 1 0 0\nv 1 1 0\nf 1 2 3\n")
+    with pytest.raises(ValueError):
+        mesh_loader.load_obj(q)

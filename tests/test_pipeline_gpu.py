@@ -190,3 +190,43 @@ def test_cuda_graph_replay_matches_eager(env):
     # a different image size or refine count is a different graph
     ok, p2 = m.Register(env["rgb"], env["depth"], env["mask"], "mustard_proxy", refine_itr=1)
     assert ok and np.isfinite(p2).all()
+
+
+def test_infer_core_boundary(tmp_path):
+    """The BaseInferCore-shaped entry points on the reference's own blob layout (f32 NHWC [n,160,160,6])."""
+    import ctypes as C
+    from foundationpose_cpp_b200 import capi
+    refiner, scorer = helpers.seeded_nets()
+    rp, sp = helpers.write_seeded_weights(str(tmp_path))
+    lib = capi.lib()
+    n = 4
+    torch.manual_seed(5)
+    a = torch.rand(n, 160, 160, 6)
+    b = torch.rand(n, 160, 160, 6)
+    a[..., 3:] = a[..., 3:] * 2 - 1
+    b[..., 3:] = b[..., 3:] * 2 - 1
+    ad, bd = a.cuda(), b.cuda()
+    core = C.c_void_p()
+    capi.check(lib.fpb200_infer_create(rp.encode(), 0, 8, 0, C.byref(core)))
+    trans = torch.zeros(n, 3, device="cuda")
+    rot = torch.zeros(n, 3, device="cuda")
+    capi.check(lib.fpb200_infer_refiner(core, C.c_void_p(ad.data_ptr()), C.c_void_p(bd.data_ptr()), n,
+                                        C.c_void_p(trans.data_ptr()), C.c_void_p(rot.data_ptr())))
+    with torch.no_grad():
+        t_ref, r_ref = refiner(nets.nhwc_to_inputs(a.half().float()), nets.nhwc_to_inputs(b.half().float()))
+    _net_close(trans.cpu().numpy(), t_ref.numpy(), "infer-core trans")
+    _net_close(rot.cpu().numpy(), r_ref.numpy(), "infer-core rot")
+    assert lib.fpb200_infer_refiner(core, C.c_void_p(ad.data_ptr()), C.c_void_p(bd.data_ptr()), 9,
+                                    C.c_void_p(trans.data_ptr()), C.c_void_p(rot.data_ptr())) == capi.ERR_INVALID
+    lib.fpb200_infer_destroy(core)
+    core = C.c_void_p()
+    capi.check(lib.fpb200_infer_create(sp.encode(), 1, 8, 0, C.byref(core)))
+    scores = torch.zeros(n, device="cuda")
+    capi.check(lib.fpb200_infer_scorer(core, C.c_void_p(ad.data_ptr()), C.c_void_p(bd.data_ptr()), n,
+                                       C.c_void_p(scores.data_ptr())))
+    with torch.no_grad():
+        s_ref = scorer(nets.nhwc_to_inputs(a.half().float()), nets.nhwc_to_inputs(b.half().float()))
+    _net_close(scores.cpu().numpy(), s_ref.numpy(), "infer-core scores")
+    lib.fpb200_infer_destroy(core)
+    bad = C.c_void_p()
+    assert lib.fpb200_infer_create(rp.encode(), 1, 8, 0, C.byref(bad)) != 0  # refiner file given as scorer
