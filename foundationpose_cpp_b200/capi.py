@@ -75,3 +75,10 @@ def debug_conv_gemm(desc: ConvDesc, repeat: int = 0) -> float:
     ms = C.c_float(0)
     check(lib().fpb200_debug_conv_gemm(C.byref(desc), C.c_int(repeat), C.byref(ms)))
     return ms.value
+
+
+def debug_attention(qkv_ptr: int, out_ptr: int, n_hyp: int, repeat: int = 0) -> float:
+    ms = C.c_float(0)
+    check(lib().fpb200_debug_attention(C.c_void_p(qkv_ptr), C.c_void_p(out_ptr), C.c_int(n_hyp), C.c_int(repeat),
+                                       C.byref(ms)))
+    return ms.value

@@ -5,6 +5,7 @@
 #include "../../include/fpb200.h"
 #include "common.h"
 #include "conv_gemm.h"
+#include "net_ops.h"
 
 using namespace fpb;
 
@@ -55,6 +56,31 @@ extern "C" int fpb200_debug_conv_gemm(const fpb200_conv_desc* c, int repeat, flo
     FPB_CUDA(launch_conv_gemm(plan, 0));  // warm-up + the result the caller checks
     FPB_CUDA(cudaEventRecord(e0, 0));
     for (int i = 0; i < repeat; ++i) FPB_CUDA(launch_conv_gemm(plan, 0));
+    FPB_CUDA(cudaEventRecord(e1, 0));
+    FPB_CUDA(cudaDeviceSynchronize());
+    float ms = 0.f;
+    FPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = repeat > 0 ? ms / repeat : 0.f;
+    return FPB200_OK;
+  } catch (const std::exception& e) {
+    return fail(FPB200_ERR_CUDA, "%s", e.what());
+  }
+}
+
+extern "C" int fpb200_debug_attention(const void* qkv, void* out, int n_hyp, int repeat, float* ms_out) {
+  try {
+    if (const char* e = attention_init()) return fail(FPB200_ERR_CUDA, "%s", e);
+    const __half* q = static_cast<const __half*>(qkv);
+    __half* o = static_cast<__half*>(out);
+    cudaEvent_t e0, e1;
+    FPB_CUDA(cudaEventCreate(&e0));
+    FPB_CUDA(cudaEventCreate(&e1));
+    launch_attention(q, o, n_hyp, 1536, 512, 0);
+    FPB_CUDA(cudaGetLastError());
+    FPB_CUDA(cudaEventRecord(e0, 0));
+    for (int i = 0; i < repeat; ++i) launch_attention(q, o, n_hyp, 1536, 512, 0);
     FPB_CUDA(cudaEventRecord(e1, 0));
     FPB_CUDA(cudaDeviceSynchronize());
     float ms = 0.f;

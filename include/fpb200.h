@@ -174,6 +174,10 @@ typedef struct {
 } fpb200_conv_desc;
 /* Runs the tcgen05 implicit-GEMM kernel once (+ `repeat` timed launches; avg ms -> *ms_out). */
 int fpb200_debug_conv_gemm(const fpb200_conv_desc* desc, int repeat, float* ms_out);
+/* Self-attention core of the refine / score transformers (inside the TensorRT engines in the
+ * reference, trt_core.cpp:367): qkv [n_hyp*400, 1536] fp16 (Q | K | V, 4 heads x 128) ->
+ * out [n_hyp*400, 512] fp16.  Runs once + `repeat` timed launches on the default stream. */
+int fpb200_debug_attention(const void* qkv, void* out, int n_hyp, int repeat, float* ms_out);
 
 const char* fpb200_last_error(void);
 
