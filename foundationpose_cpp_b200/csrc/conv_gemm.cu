@@ -1,10 +1,12 @@
 // tcgen05 implicit-GEMM convolution kernel (see conv_gemm.h).
 //
 // Roles inside one persistent CTA (320 threads, one CTA per SM):
-//   warp 0, lane 0 : TMA producer.  Per k-block (one filter tap x 64 input channels) it loads a
-//                    128-row activation box and a block_n-row weight box into a smem ring.
-//   warp 1, lane 0 : MMA issuer.  Four 128 x block_n x 16 tcgen05.mma per k-block, accumulating in
-//                    one of two TMEM accumulator stages.
+//   warp 0         : TMA producer.  Two rings: activation BLOCKS (one per tap group x 64 input
+//                    channels: bh + span tile rows, loaded once and shared by the group's taps) and
+//                    weight stages (one block_n-row tile per tap).
+//   warp 1         : MMA issuer.  Four 128 x block_n x 16 tcgen05.mma per tap, the activation operand
+//                    descriptor shifted by the tap's row offset inside the block, accumulating in one
+//                    of two TMEM accumulator stages.
 //   warps 2..9     : epilogue.  tcgen05.ld 32 columns at a time, transpose through shared memory so
 //                    that global accesses are row-contiguous, bias / residual / ReLU / pos-table.
 // The two TMEM stages let the epilogue of tile i overlap the MMAs of tile i+1.
@@ -21,48 +23,39 @@ namespace fpb {
 namespace {
 
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
-constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KB
 constexpr int kStageBytesPerWarp = 32 * 32 * 4;         // epilogue staging: 32 rows x 32 fp32 columns
+constexpr int kMaxRing = 8;
+constexpr int kBarrierBytes = 1024;  // mbarriers, TMEM slot, the issuer's K-loop schedule
+constexpr int kSchedMax = 96;        // taps x 64-channel blocks of one tile (per-tap kernels)
+constexpr int kSmemBudget = 232448 - 1024 - 8 * kStageBytesPerWarp - kBarrierBytes;  // for the two rings
 
-// MODE 0: independent CTAs.  MODE 1: CTA pairs, each CTA loads half of the weight tile and
-// multicasts it to both (halves the L2 reads of B; each SM still ingests A + B).  MODE 2: CTA pairs
-// issuing ONE tcgen05.mma.cta_group::2 of M = 256: each SM holds (and ingests) its 128 activation
-// rows and only HALF of the weight tile, which is what lifts the shared-memory fill-rate bound of the
-// narrower tiles.
-template <int BN, int MODE>
+// PAIR = false: independent CTAs.  PAIR = true: CTA pairs issuing ONE tcgen05.mma.cta_group::2 of
+// M = 256: each SM holds (and ingests) its 128 activation rows and only HALF of the weight tile.
+template <int BN, bool PAIR>
 struct Cfg {
-  static constexpr int kCS = MODE == 0 ? 1 : 2;
-  static constexpr int kBBytes = (BN * kGemmBlockK * 2) / (MODE == 2 ? 2 : 1);  // per CTA and k-block
-  // k-blocks per pipeline stage: the producer / MMA warps synchronise once per stage, and that
-  // hand-shake (try_wait + fence + elect + commit, ~500 cycles of warp time) has to be covered by the
-  // tensor-core time of the stage: 4 MMAs of N=256 cover it, 4 MMAs of N<=128 do not.
-  static constexpr int kKS = BN == 256 ? 1 : 2;
-  static constexpr int kStageBytes = kKS * (kABytes + kBBytes);
-  static constexpr int kStages = (192 * 1024) / kStageBytes > 10 ? 10 : (192 * 1024) / kStageBytes;
+  static constexpr int kCS = PAIR ? 2 : 1;
+  static constexpr int kBTile = (BN * kGemmBlockK * 2) / kCS;  // weight bytes per CTA and tap
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr size_t kSmem = 1024 /*alignment slack*/ + size_t(kStages) * kStageBytes +
-                                  8 * kStageBytesPerWarp /*epilogue staging*/ + 256 /*barriers*/;
 };
 
-template <int BN, int MODE>
+template <int BN, bool PAIR, bool PER_TAP>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using C = Cfg<BN, MODE>;
+  using C = Cfg<BN, PAIR>;
   constexpr int CS = C::kCS;
-  constexpr bool kPairMma = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr int KS = C::kKS;
-  const uint32_t a_base = smem_base;                                // [stage][sub] activation tiles
-  const uint32_t b_base = smem_base + C::kStages * KS * kABytes;    // [stage][sub] weight tiles
-  const uint32_t stage_base = b_base + C::kStages * KS * C::kBBytes;
+  const uint32_t a_base = smem_base;                        // [na] activation blocks
+  const uint32_t b_base = a_base + p.na * p.a_bytes;        // [nb] weight stages
+  const uint32_t stage_base = b_base + p.nb * p.b_stage_bytes;
   const uint32_t bar_base = stage_base + 8 * kStageBytesPerWarp;
-  // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem ptr
+  // barrier layout (8 B each): full[8], empty[8], tfull[2], tempty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxRing + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxRing + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxRing + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxRing + 4);
+  const uint32_t sched_base = bar_base + 256;  // kSchedMax x u32
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
       smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -70,23 +63,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) {
-      // MODE 2: the leader's full barrier takes one expect_tx arrival from each CTA's producer
-      ptx::mbar_init(full_bar(s), kPairMma ? 2 : 1);
-      // MODE 1: one tcgen05.commit arrival from every CTA; MODE 2: one multicast commit by the leader
-      ptx::mbar_init(empty_bar(s), MODE == 1 ? 2 : 1);
+    for (int s = 0; s < kMaxRing; ++s) {
+      // PAIR: the leader's full barriers take one expect_tx arrival from each CTA's producer; the
+      // empty barriers one multicast tcgen05.commit by the leader
+      ptx::mbar_init(full_bar(s), PAIR ? 2 : 1);
+      ptx::mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      // one arrival per epilogue warp (MODE 2: of both CTAs, on the leader's barrier)
-      ptx::mbar_init(tempty_bar(s), kPairMma ? 16 : 8);
+      // one arrival per epilogue warp (PAIR: of both CTAs, on the leader's barrier)
+      ptx::mbar_init(tempty_bar(s), PAIR ? 16 : 8);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tm_a);
     ptx::prefetch_tensormap(&p.tm_b);
   }
   if (warp == 1) {
-    if (kPairMma) {
+    if (PAIR) {
       ptx::tmem_alloc_pair(tmem_slot, C::kTmemCols);
       ptx::tmem_relinquish_pair();
     } else {
@@ -96,105 +89,190 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CS > 1) ptx::cluster_sync();  // peers' barriers are initialised before anything is multicast
+  if (CS > 1) ptx::cluster_sync();  // the peer's barriers are initialised before anything lands on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_img;
   const int m_groups = (m_tiles + CS - 1) / CS;
   const int total_tiles = m_groups * p.n_tiles;  // work items of a cluster
-  const int kblocks = p.num_taps * p.cblocks;
   const int crank = CS > 1 ? (int)ptx::cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / CS;
   const int num_clusters = gridDim.x / CS;
   constexpr uint16_t kAllCtas = (uint16_t)((1u << CS) - 1u);
-  constexpr int n_stages = C::kStages;
 
+  const int items = p.cblocks * p.num_groups;        // K-loop items of a tile
   if (warp == 0) {
-    {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int nt = tile % p.n_tiles;
-        const int mt = (tile / p.n_tiles) * CS + crank;  // may be >= m_tiles: TMA zero-fills, epilogue masks
-        const int x0 = (mt % p.tiles_x) * p.bw;
-        const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
-        const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
-        for (int kb0 = 0; kb0 < kblocks; kb0 += KS) {
-          const int nsub = min(KS, kblocks - kb0);
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+    int as = 0, bs = 0;
+    uint32_t bph = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) * CS + crank;  // may be >= m_tiles: TMA zero-fills, epilogue masks
+      const int x0 = (mt % p.tiles_x) * p.bw;
+      const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
+      const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
+      const int nrow = nt * BN + crank * (BN / CS);
+      int cb = 0, g = 0;
+      for (int j = 0; j < items; ++j) {
+        const int ntap = p.g_ntaps[g];
+        const uint32_t kidx = p.g_kidx[g];
+        const int ax = x0 + p.g_dx[g], ay = y0 + p.g_dy[g], ap = p.g_plane[g];
+        const uint32_t a_dst = a_base + as * p.a_bytes;
+        as = (as + 1 == p.na) ? 0 : as + 1;
+        const int nstage = PER_TAP ? ntap : 1;
+        for (int i = 0; i < nstage; ++i) {
+          ptx::mbar_wait(empty_bar(bs), bph ^ 1u);
           if (ptx::elect_one()) {
-            const uint32_t bytes = nsub * (kABytes + C::kBBytes);
-            // MODE 2: both CTAs report their bytes to (and land their loads on) the LEADER's barrier
-            const uint32_t bar = kPairMma ? ptx::mapa_rank(full_bar(stage), 0) : full_bar(stage);
-            if (kPairMma) ptx::mbar_expect_tx_cluster(bar, bytes);
+            // PAIR: both CTAs report their bytes to (and land their loads on) the LEADER's barrier
+            const uint32_t bar = PAIR ? ptx::mapa_rank(full_bar(bs), 0) : full_bar(bs);
+            const uint32_t bytes = (i == 0 ? p.a_bytes : 0) + (PER_TAP ? 1 : ntap) * C::kBTile;
+            if (PAIR) ptx::mbar_expect_tx_cluster(bar, bytes);
             else ptx::mbar_expect_tx(bar, bytes);
-            for (int sub = 0; sub < nsub; ++sub) {
-              const int kb = kb0 + sub;
-              const int t = kb / p.cblocks, cb = kb - t * p.cblocks;
-              const int cx = x0 + p.tap_dx[t], cy = y0 + p.tap_dy[t], cp = p.tap_plane[t];
-              const uint32_t a_dst = a_base + (stage * KS + sub) * kABytes;
-              const uint32_t b_dst = b_base + (stage * KS + sub) * C::kBBytes;
-              if (kPairMma) {
-                ptx::tma_load_5d_pair(a_dst, &p.tm_a, bar, cb * kGemmBlockK, cx, cy, cp, n0);
-                ptx::tma_load_2d_pair(b_dst, &p.tm_b, bar, kb * kGemmBlockK, nt * BN + crank * (BN / 2));
-              } else {
-                ptx::tma_load_5d(a_dst, &p.tm_a, bar, cb * kGemmBlockK, cx, cy, cp, n0);
-                if (MODE == 0) ptx::tma_load_2d(b_dst, &p.tm_b, bar, kb * kGemmBlockK, nt * BN);
-                else ptx::tma_load_2d_mcast(b_dst + crank * (C::kBBytes / 2), &p.tm_b, bar, kb * kGemmBlockK,
-                                            nt * BN + crank * (BN / 2), kAllCtas);
-              }
+            if (i == 0) {
+              if (PAIR) ptx::tma_load_5d_pair(a_dst, &p.tm_a, bar, cb * kGemmBlockK, ax, n0, ay, ap);
+              else ptx::tma_load_5d(a_dst, &p.tm_a, bar, cb * kGemmBlockK, ax, n0, ay, ap);
+            }
+            const uint32_t b_dst = b_base + bs * p.b_stage_bytes;
+            const int t0 = PER_TAP ? i : 0, t1 = PER_TAP ? i + 1 : ntap;
+            for (int t = t0; t < t1; ++t) {
+              const int kcol = (((kidx >> (8 * t)) & 0xff) * p.cblocks + cb) * kGemmBlockK;
+              const uint32_t dst = b_dst + (PER_TAP ? 0 : t) * C::kBTile;
+              if (PAIR) ptx::tma_load_2d_pair(dst, &p.tm_b, bar, kcol, nrow);
+              else ptx::tma_load_2d(dst, &p.tm_b, bar, kcol, nrow);
             }
           }
           __syncwarp();
-          if (++stage == n_stages) {
-            stage = 0;
-            phase ^= 1u;
+          if (++bs == p.nb) {
+            bs = 0;
+            bph ^= 1u;
           }
+        }
+        if (++g == p.num_groups) {
+          g = 0;
+          if (++cb == p.cblocks) cb = 0;
         }
       }
     }
   } else if (warp == 1) {
-    if (!kPairMma || crank == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(kPairMma ? 256 : kGemmBlockM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
+    if (!PAIR || crank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(PAIR ? 256 : kGemmBlockM, BN);
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SWIZZLE_128B
+      const uint32_t row_units = p.row_bytes >> 4;  // descriptor address units are 16 bytes
+      const uint32_t a_units = p.a_bytes >> 4, b_units = p.b_stage_bytes >> 4;
+      const uint32_t a_lo0 = ((a_base & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((b_base & 0x3FFFF) >> 4) | (1u << 16);
+      auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+      int as = 0, bs = 0;
+      uint32_t bph = 0;
       int it = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb0 = 0; kb0 < kblocks; kb0 += KS) {
-          const int nsub = min(KS, kblocks - kb0);
-          ptx::mbar_wait(full_bar(stage), phase);
+      if constexpr (PER_TAP) {
+        // K-loop schedule of a tile, one entry per tap: descriptor offset of the tap inside its
+        // activation block | bit 16: first tap of a group (next activation slot)
+        volatile uint32_t* sched = reinterpret_cast<volatile uint32_t*>(
+            smem_raw + (sched_base - ptx::smem_u32(smem_raw)));
+        const int taps_cb = [&] {
+          int n = 0;
+          for (int g = 0; g < p.num_groups; ++g) n += p.g_ntaps[g];
+          return n;
+        }();
+        if (lane == 0) {
+          int n = 0;
+          for (int g = 0; g < p.num_groups; ++g)
+            for (int i = 0; i < p.g_ntaps[g]; ++i)
+              sched[n++] = (((p.g_aoff[g] >> (8 * i)) & 0xff) * row_units) | (i == 0 ? 1u << 16 : 0u);
+        }
+        __syncwarp();
+        const int n_entries = taps_cb * p.cblocks;
+        uint32_t a_cur = a_lo0;
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            for (int sub = 0; sub < nsub; ++sub) {
-              const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_base + (stage * KS + sub) * kABytes);
-              const uint64_t bdesc = ptx::make_sw128_kmajor_desc(b_base + (stage * KS + sub) * C::kBBytes);
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          uint32_t first = 0;  // 0 until the first MMA of the tile has been issued
+          int si = 0;
+          uint32_t e = sched[0];
+          for (int idx = 0; idx < n_entries; ++idx) {
+            if (++si == taps_cb) si = 0;
+            const uint32_t e_next = sched[si];
+            if (e & (1u << 16)) {
+              a_cur = a_lo0 + as * a_units;
+              as = (as + 1 == p.na) ? 0 : as + 1;
+            }
+            const uint64_t adesc = desc(a_cur + (e & 0xffffu));
+            const uint64_t bdesc = desc(b_lo0 + bs * b_units);
+            ptx::mbar_wait(full_bar(bs), bph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
 #pragma unroll
               for (int k = 0; k < kGemmBlockK / 16; ++k) {
                 // advancing 16 fp16 along K inside the 128-byte swizzle row = +32 B = +2 in the
                 // descriptor's 16-byte address units
-                const uint32_t accum = (kb0 | sub | k) != 0;
-                if (kPairMma) ptx::umma_f16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
-                else ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
+                if (PAIR) ptx::umma_f16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, first | (uint32_t)k);
+                else ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, first | (uint32_t)k);
+              }
+              if (PAIR) ptx::umma_commit_pair_mcast(empty_bar(bs), kAllCtas);
+              else ptx::umma_commit(empty_bar(bs));
+              if (idx == n_entries - 1) {
+                if (PAIR) ptx::umma_commit_pair_mcast(tfull_bar(acc), kAllCtas);
+                else ptx::umma_commit(tfull_bar(acc));
               }
             }
-            if (MODE == 0) ptx::umma_commit(empty_bar(stage));
-            else if (MODE == 1) ptx::umma_commit_mcast(empty_bar(stage), kAllCtas);
-            else ptx::umma_commit_pair_mcast(empty_bar(stage), kAllCtas);
-            if (kb0 + KS >= kblocks) {
-              if (kPairMma) ptx::umma_commit_pair_mcast(tfull_bar(acc), kAllCtas);
-              else ptx::umma_commit(tfull_bar(acc));
+            __syncwarp();
+            first = 1;
+            e = e_next;
+            if (++bs == p.nb) {
+              bs = 0;
+              bph ^= 1u;
             }
           }
-          __syncwarp();
-          if (++stage == n_stages) {
-            stage = 0;
-            phase ^= 1u;
+        }
+      } else {
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          uint32_t first = 0;
+          int g = 0;
+          for (int j = 0; j < items; ++j) {
+            const int ntap = p.g_ntaps[g];
+            const uint32_t aoff = p.g_aoff[g];
+            const uint32_t a_cur = a_lo0 + as * a_units;
+            as = (as + 1 == p.na) ? 0 : as + 1;
+            const uint32_t b_cur = b_lo0 + bs * b_units;
+            ptx::mbar_wait(full_bar(bs), bph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int i = 0; i < kMaxGroupTaps; ++i) {
+                if (i < ntap) {
+                  const uint64_t adesc = desc(a_cur + ((aoff >> (8 * i)) & 0xff) * row_units);
+                  const uint64_t bdesc = desc(b_cur + i * (C::kBTile >> 4));
+#pragma unroll
+                  for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                    const uint32_t accum = first | (uint32_t)(i | k);
+                    if (PAIR) ptx::umma_f16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
+                    else ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
+                  }
+                }
+              }
+              if (PAIR) ptx::umma_commit_pair_mcast(empty_bar(bs), kAllCtas);
+              else ptx::umma_commit(empty_bar(bs));
+              if (j == items - 1) {
+                if (PAIR) ptx::umma_commit_pair_mcast(tfull_bar(acc), kAllCtas);
+                else ptx::umma_commit(tfull_bar(acc));
+              }
+            }
+            __syncwarp();
+            first = 1;
+            if (++bs == p.nb) {
+              bs = 0;
+              bph ^= 1u;
+            }
+            if (++g == p.num_groups) g = 0;
           }
         }
       }
@@ -220,8 +298,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int nt = tile % p.n_tiles;
       const int mt = (tile / p.n_tiles) * CS + crank;
       const int x0 = (mt % p.tiles_x) << p.bw_log2;
-      const int y0 = ((mt / p.tiles_x) % p.tiles_y) << p.bh_log2;
-      const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
+      const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
+      const int n0 = (mt / (p.tiles_x * p.tiles_y)) << p.bn_log2;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       // per-lane bookkeeping for the 4 row groups (offsets in units of 8 halves = 16 bytes)
@@ -229,10 +307,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t vmask = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int row = q * 32 + i * 8 + sub;
+        const int row = q * 32 + i * 8 + sub;  // GEMM row = (y * bn + n) * bw + x
         const int x = x0 + (row & (p.bw - 1));
-        const int y = y0 + ((row >> p.bw_log2) & (p.bh - 1));
-        const int n = n0 + (row >> (p.bw_log2 + p.bh_log2));
+        const int n = n0 + ((row >> p.bw_log2) & (p.bn - 1));
+        const int y = y0 + (row >> (p.bw_log2 + p.bn_log2));
         if ((x < p.W) && (y < p.H) && (n < p.n_img)) vmask |= 1u << i;
         const int nn = n % p.img_mod;
         const int coff = (n / p.img_mod) * p.half_coff + nt * BN;
@@ -326,7 +404,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (kPairMma) ptx::mbar_arrive_cluster(ptx::mapa_rank(tempty_bar(acc), 0));
+        if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa_rank(tempty_bar(acc), 0));
         else ptx::mbar_arrive(tempty_bar(acc));
       }
     }
@@ -337,7 +415,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (CS > 1) ptx::cluster_sync();  // no CTA exits while a peer may still signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
-    if (kPairMma) ptx::tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, C::kTmemCols);
     else ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
@@ -359,18 +437,19 @@ const char* conv_gemm_init() {
   if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
     return "cuTensorMapEncodeTiled not available from the CUDA driver";
   e = cudaSuccess;
-  auto set_attr = [&](auto kernel, size_t smem) {
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto set_attr = [&](auto kernel) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   };
-  set_attr(conv_gemm_kernel<64, 0>, Cfg<64, 0>::kSmem);
-  set_attr(conv_gemm_kernel<128, 0>, Cfg<128, 0>::kSmem);
-  set_attr(conv_gemm_kernel<256, 0>, Cfg<256, 0>::kSmem);
-  set_attr(conv_gemm_kernel<64, 1>, Cfg<64, 1>::kSmem);
-  set_attr(conv_gemm_kernel<128, 1>, Cfg<128, 1>::kSmem);
-  set_attr(conv_gemm_kernel<256, 1>, Cfg<256, 1>::kSmem);
-  set_attr(conv_gemm_kernel<64, 2>, Cfg<64, 2>::kSmem);
-  set_attr(conv_gemm_kernel<128, 2>, Cfg<128, 2>::kSmem);
-  set_attr(conv_gemm_kernel<256, 2>, Cfg<256, 2>::kSmem);
+  set_attr(conv_gemm_kernel<64, false, false>);
+  set_attr(conv_gemm_kernel<64, false, true>);
+  set_attr(conv_gemm_kernel<64, true, false>);
+  set_attr(conv_gemm_kernel<64, true, true>);
+  set_attr(conv_gemm_kernel<128, false, false>);
+  set_attr(conv_gemm_kernel<128, false, true>);
+  set_attr(conv_gemm_kernel<128, true, false>);
+  set_attr(conv_gemm_kernel<128, true, true>);
+  set_attr(conv_gemm_kernel<256, false, true>);
+  set_attr(conv_gemm_kernel<256, true, true>);
   if (e != cudaSuccess) return "cudaFuncSetAttribute(max dynamic smem) failed (not an sm_100a device?)";
   int dev = 0;
   cudaGetDevice(&dev);
@@ -429,24 +508,98 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   if (out_ld % 8 || d.half_coff % 8) return "conv_gemm: output leading dims must be multiples of 8";
   if (d.out_phase_split && ((d.out_h | d.out_w) & 1)) return "conv_gemm: phase-split needs even H, W";
 
-  // pairing mode (see Cfg): 0 = single CTAs, 1 = pair + weight multicast, 2 = pair + cta_group::2 MMA
+  // pairing mode (see Cfg): 0 = single CTAs, 2 = CTA pairs issuing cta_group::2 MMAs
   const long long m_tiles_all = (long long)((d.out_w + d.bw - 1) / d.bw) * ((d.out_h + d.bh - 1) / d.bh) *
                                 ((d.n_img + d.bn - 1) / d.bn);
-  int mode = d.cluster > 0 ? d.cluster - 1 : (m_tiles_all >= 2 * g_num_sms ? 2 : 0);
-  if (const char* env = getenv("FPB_GEMM_MODE")) mode = atoi(env);
-  if (mode < 0 || mode > 2) return "conv_gemm: pairing mode must be 0, 1 or 2";
+  int mode = d.cluster > 0 ? (d.cluster == 1 ? 0 : 2) : (m_tiles_all >= 2 * g_num_sms ? 2 : 0);
+  if (const char* env = getenv("FPB_GEMM_MODE")) mode = atoi(env) ? 2 : 0;
   const int cluster = mode == 0 ? 1 : 2;
+  if (d.bn & (d.bn - 1)) return "conv_gemm: bn must be a power of two";
+  if ((d.bw * d.bn) % 8) return "conv_gemm: a tile row (bw*bn pixels) must be a whole number of swizzle atoms";
   ConvGemmParams& p = plan->p;
   memset(&p, 0, sizeof(p));
+  // ---- tap groups: taps with the same (dx, plane) share one activation block
+  int span = 0;
+  {
+    int num_groups = 0;
+    int g_dx[kMaxGroups], g_plane[kMaxGroups], g_dy[kMaxGroups], dy_max[kMaxGroups], g_ntaps[kMaxGroups] = {0};
+    int g_tap[kMaxGroups][kMaxGroupTaps];
+    for (int t = 0; t < d.num_taps; ++t) {
+      int g = 0;
+      for (; g < num_groups; ++g)
+        if (g_dx[g] == d.tap_dx[t] && g_plane[g] == d.tap_plane[t]) break;
+      if (g == num_groups) {
+        if (g == kMaxGroups) return "conv_gemm: too many tap groups";
+        num_groups++;
+        g_dx[g] = d.tap_dx[t];
+        g_plane[g] = d.tap_plane[t];
+        g_dy[g] = dy_max[g] = d.tap_dy[t];
+      }
+      if (g_ntaps[g] == kMaxGroupTaps) return "conv_gemm: too many taps in a group";
+      g_tap[g][g_ntaps[g]++] = t;
+      if (d.tap_dy[t] < g_dy[g]) g_dy[g] = d.tap_dy[t];
+      if (d.tap_dy[t] > dy_max[g]) dy_max[g] = d.tap_dy[t];
+    }
+    int max_taps = 1;
+    for (int g = 0; g < num_groups; ++g) {
+      if (dy_max[g] - g_dy[g] > span) span = dy_max[g] - g_dy[g];
+      if (g_ntaps[g] > max_taps) max_taps = g_ntaps[g];
+    }
+    if (d.bh + span > 256) return "conv_gemm: activation block too tall";
+    p.row_bytes = d.bn * d.bw * 128;
+    p.a_bytes = (d.bh + span) * p.row_bytes;
+    const int b_tile = bn_tile * kGemmBlockK * 2 / cluster;
+    // one weight stage per tap when a tap alone covers the producer/issuer hand-shake (>= 16 KB of
+    // weights = 4 MMAs of N = 256), else one stage per group
+    const bool per_tap = b_tile >= 16384 || max_taps == 1;
+    p.b_stage_bytes = (per_tap ? 1 : max_taps) * b_tile;
+    int uses[kMaxGroups];
+    for (int g = 0; g < num_groups; ++g) uses[g] = per_tap ? g_ntaps[g] : 1;
+    // ring depths: most weight stages such that an activation slot is provably free when reused
+    p.na = p.nb = 0;
+    for (int na = 2; na <= kMaxRing; ++na) {
+      const long long left = (long long)kSmemBudget - (long long)na * p.a_bytes;
+      if (left < 2LL * p.b_stage_bytes) break;
+      int nb = (int)(left / p.b_stage_bytes);
+      int cond = 1 << 30;  // weight stages in any na-1 consecutive groups
+      for (int g0 = 0; g0 < num_groups; ++g0) {
+        int sum = 0;
+        for (int j = 0; j < na - 1; ++j) sum += uses[(g0 + j) % num_groups];
+        if (sum < cond) cond = sum;
+      }
+      if (cond < nb) nb = cond;
+      if (nb > kMaxRing) nb = kMaxRing;
+      if (nb > p.nb) {
+        p.nb = nb;
+        p.na = na;
+      }
+    }
+    if (p.nb < 2) return "conv_gemm: tile does not fit in shared memory";
+    p.num_groups = num_groups;
+    p.per_tap = per_tap ? 1 : 0;
+    if (per_tap && d.num_taps * (d.cin / kGemmBlockK) > kSchedMax) return "conv_gemm: K loop too long";
+    for (int g = 0; g < num_groups; ++g) {
+      p.g_dx[g] = (int8_t)g_dx[g];
+      p.g_dy[g] = (int8_t)g_dy[g];
+      p.g_plane[g] = (int8_t)g_plane[g];
+      p.g_ntaps[g] = (int8_t)g_ntaps[g];
+      for (int i = 0; i < g_ntaps[g]; ++i) {
+        const int t = g_tap[g][i];
+        p.g_aoff[g] |= (uint32_t)(d.tap_dy[t] - g_dy[g]) << (8 * i);
+        p.g_kidx[g] |= (uint32_t)t << (8 * i);
+      }
+    }
+  }
   {
     const long long sw = d.stride_w ? d.stride_w : 2LL * d.cin;
     const long long sh = d.stride_h ? d.stride_h : sw * d.in_w;
     const long long sp = d.stride_plane ? d.stride_plane : sh * d.in_h;
     const long long si = d.stride_img ? d.stride_img : sp * d.planes;
-    cuuint64_t dims[5] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.in_h,
-                          (cuuint64_t)d.planes, (cuuint64_t)d.n_img};
-    cuuint64_t strides[4] = {(cuuint64_t)sw, (cuuint64_t)sh, (cuuint64_t)sp, (cuuint64_t)si};
-    cuuint32_t box[5] = {kGemmBlockK, (cuuint32_t)d.bw, (cuuint32_t)d.bh, 1, (cuuint32_t)d.bn};
+    // dimension order (C, W, image, H, plane): the box lands in shared memory as [h][image][w] rows
+    cuuint64_t dims[5] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.n_img, (cuuint64_t)d.in_h,
+                          (cuuint64_t)d.planes};
+    cuuint64_t strides[4] = {(cuuint64_t)sw, (cuuint64_t)si, (cuuint64_t)sh, (cuuint64_t)sp};
+    cuuint32_t box[5] = {kGemmBlockK, (cuuint32_t)d.bw, (cuuint32_t)d.bn, (cuuint32_t)(d.bh + span), 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)d.in, dims, strides,
                           box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -477,7 +630,7 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   p.bh = d.bh;
   p.bn = d.bn;
   for (p.bw_log2 = 0; (1 << p.bw_log2) < d.bw; ++p.bw_log2) {}
-  for (p.bh_log2 = 0; (1 << p.bh_log2) < d.bh; ++p.bh_log2) {}
+  for (p.bn_log2 = 0; (1 << p.bn_log2) < d.bn; ++p.bn_log2) {}
   p.W = d.out_w;
   p.H = d.out_h;
   p.n_img = d.n_img;
@@ -485,11 +638,7 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   p.tiles_y = (d.out_h + d.bh - 1) / d.bh;
   p.tiles_img = (d.n_img + d.bn - 1) / d.bn;
   p.n_tiles = d.cout / bn_tile;
-  p.num_taps = d.num_taps;
   p.cblocks = d.cin / kGemmBlockK;
-  memcpy(p.tap_dx, d.tap_dx, sizeof(p.tap_dx));
-  memcpy(p.tap_dy, d.tap_dy, sizeof(p.tap_dy));
-  memcpy(p.tap_plane, d.tap_plane, sizeof(p.tap_plane));
   p.bias = d.bias;
   p.residual = d.residual;
   p.res_ld = d.res_ld ? d.res_ld : d.cout;
@@ -509,18 +658,13 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   const long long work = ((m_tiles + cluster - 1) / cluster) * p.n_tiles;  // per cluster
   const int cap = (d.max_ctas > 0 ? d.max_ctas : g_num_sms) / cluster;
   plan->grid = (int)(work < cap ? work : cap) * cluster;
-  {
-    const size_t sm[3][3] = {{Cfg<64, 0>::kSmem, Cfg<64, 1>::kSmem, Cfg<64, 2>::kSmem},
-                             {Cfg<128, 0>::kSmem, Cfg<128, 1>::kSmem, Cfg<128, 2>::kSmem},
-                             {Cfg<256, 0>::kSmem, Cfg<256, 1>::kSmem, Cfg<256, 2>::kSmem}};
-    plan->smem = sm[bn_tile == 256 ? 2 : (bn_tile == 128 ? 1 : 0)][mode];
-  }
+  plan->smem = 1024 + (size_t)p.na * p.a_bytes + (size_t)p.nb * p.b_stage_bytes + 8 * kStageBytesPerWarp + kBarrierBytes;
   plan->flops = 2.0 * d.n_img * d.out_h * d.out_w * (double)d.cout * d.num_taps * d.cin;
   return nullptr;
 }
 
 namespace {
-template <int BN, int MODE>
+template <int BN, bool PAIR, bool PER_TAP>
 cudaError_t launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan.grid);
@@ -529,19 +673,21 @@ cudaError_t launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = Cfg<BN, MODE>::kCS;
+  attr[0].val.clusterDim.x = Cfg<BN, PAIR>::kCS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, MODE>, plan.p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, PAIR, PER_TAP>, plan.p);
 }
 template <int BN>
 cudaError_t launch_bn(const ConvGemmPlan& plan, cudaStream_t stream) {
-  switch (plan.mode) {
-    case 2: return launch_one<BN, 2>(plan, stream);
-    case 1: return launch_one<BN, 1>(plan, stream);
-    default: return launch_one<BN, 0>(plan, stream);
+  const bool pair = plan.mode == 2;
+  if constexpr (BN == 256) {
+    return pair ? launch_one<BN, true, true>(plan, stream) : launch_one<BN, false, true>(plan, stream);
+  } else {
+    if (plan.p.per_tap) return pair ? launch_one<BN, true, true>(plan, stream) : launch_one<BN, false, true>(plan, stream);
+    return pair ? launch_one<BN, true, false>(plan, stream) : launch_one<BN, false, false>(plan, stream);
   }
 }
 }  // namespace

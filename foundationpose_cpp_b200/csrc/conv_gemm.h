@@ -3,9 +3,11 @@
 // One kernel serves every GEMM-shaped layer of the refine and score networks (SURVEY.md §2.3;
 // the reference runs them inside TensorRT: easy_deploy_tool/inference_core/trt_core/src/trt_core.cpp:323-371):
 //   * 3x3 / 7x7 convolutions, stride 1 or 2, NHWC fp16 activations, as a sum over filter taps of
-//     [128 pixels x 64 channels] x [64 channels x Cout] products.  The activation tile of a tap is
-//     one TMA box of a 5-D view (C, W, H, plane, image) of the input; zero padding is TMA
-//     out-of-bounds fill.  Stride-2 layers read an input that its producer wrote phase-split
+//     [128 pixels x 64 channels] x [64 channels x Cout] products.  Taps that differ only in their
+//     vertical offset share ONE activation block in shared memory (a TMA box of bh + span tile rows
+//     of a 5-D view (C, W, image, H, plane) of the input; zero padding is TMA out-of-bounds fill)
+//     and address it through shifted operand descriptors, which cuts the L2 -> SM activation
+//     traffic of a 3x3 layer 2.4x.  Stride-2 layers read an input that its producer wrote phase-split
 //     (plane = (y&1)*2 + (x&1)), which makes every tap a unit-stride box again.
 //   * linear layers (1 tap, W = number of rows).
 // Epilogue (fused): + bias, + residual, ReLU, + positional table, fp16 store with optional
@@ -22,18 +24,35 @@ constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;
 constexpr int kMaxTaps = 16;
 
+constexpr int kMaxGroups = 8;     // tap groups per layer (taps that share dx and plane)
+constexpr int kMaxGroupTaps = 4;  // taps per group (differ only in dy)
+
 struct ConvGemmParams {
-  CUtensorMap tm_a;  // activations, 5-D (C, W, H, plane, image), box (64, bw, bh, 1, bn)
-  CUtensorMap tm_b;  // weights, 2-D (K_total, Cout), box (64, block_n)
-  // M tiling: a tile is bw x bh pixels of bn consecutive images (bw*bh*bn == 128).
+  CUtensorMap tm_a;  // activations, 5-D (C, W, image, H, plane), box (64, bw, bn, bh + span, 1)
+  CUtensorMap tm_b;  // weights, 2-D (K_total, Cout), box (64, block_n or block_n / 2)
+  // M tiling: a tile is bw x bh pixels of bn consecutive images (bw*bh*bn == 128); GEMM row
+  // r = (y * bn + n) * bw + x, so that one tile row (bn*bw pixels) is a whole number of 1024-byte
+  // swizzle atoms and a vertical filter offset is an aligned shift of the operand start address.
   int tiles_x, tiles_y, tiles_img;
   int bw, bh, bn;
-  int bw_log2, bh_log2;
+  int bw_log2, bn_log2;
   int W, H, n_img;  // output extent (validity of rows)
   int n_tiles;      // Cout / block_n
-  int num_taps;     // filter taps
   int cblocks;      // input channel blocks of 64 per tap
-  int8_t tap_dx[kMaxTaps], tap_dy[kMaxTaps], tap_plane[kMaxTaps];
+  // K loop = (64-channel block, tap group) items; the taps of a group read the same activation
+  // block (bh + span tile rows, loaded ONCE) at different row offsets, each with its own weight tile.
+  // Weight stages (one tile, or all tiles of a group) are the only synchronised ring: an activation
+  // block rides on the full-barrier of its group's first weight stage, and its slot is known to be
+  // free again because the ring depths satisfy (weight stages in any na-1 consecutive groups) >= nb.
+  int num_groups;
+  int per_tap;      // 1: one weight stage per tap; 0: one per group
+  int a_bytes;      // bytes of one activation block
+  int row_bytes;    // bytes of one tile row (bn * bw * 128)
+  int na, nb;       // ring depths: activation blocks / weight stages
+  int b_stage_bytes;
+  int8_t g_dx[kMaxGroups], g_dy[kMaxGroups], g_plane[kMaxGroups], g_ntaps[kMaxGroups];
+  uint32_t g_aoff[kMaxGroups];  // 4 x 8 bit: tile-row offset of each tap inside the block
+  uint32_t g_kidx[kMaxGroups];  // 4 x 8 bit: index of each tap in the weight tensor
   // epilogue
   const float* bias;       // [Cout] fp32
   const __half* residual;  // [n_img, H, W, res_ld] fp16 or nullptr
@@ -72,15 +91,15 @@ struct ConvGemmDesc {
   int img_mod = 0;  // 0 -> n_img
   int half_coff = 0;
   int max_ctas = 0;  // 0 -> number of SMs
-  int cluster = 0;   // 0 -> automatic; 1 = single CTAs; 2 = CTA pairs + weight multicast;
-                     // 3 = CTA pairs issuing tcgen05.mma.cta_group::2 (M = 256)
+  int cluster = 0;   // 0 -> automatic; 1 = single CTAs; 2, 3 = CTA pairs issuing
+                     // tcgen05.mma.cta_group::2 (M = 256)
 };
 
 struct ConvGemmPlan {
   ConvGemmParams p;
   int block_n = 0;
   int cluster = 1;  // CTAs per cluster
-  int mode = 0;     // 0 single, 1 pair + multicast, 2 pair + cta_group::2
+  int mode = 0;     // 0 single CTAs, 2 CTA pairs + cta_group::2
   int grid = 0;
   size_t smem = 0;
   double flops = 0;  // 2*M*N*K over valid rows

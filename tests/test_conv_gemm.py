@@ -12,7 +12,7 @@ from foundationpose_cpp_b200 import capi, layouts
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 2, 3], ids=["cta", "pair_mcast", "pair_umma2"])
+@pytest.fixture(params=[1, 3], ids=["cta", "pair_umma2"])
 def cluster(request):
     return request.param
 
