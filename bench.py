@@ -261,8 +261,6 @@ def main():
 
     # ---- timed region 1: device-resident inputs, CUDA events on the launching stream
     clocks = ClockSampler(local_rank)
-    model.set_gemm_profile(True)
-    model.gemm_profile()  # clear
     launches0 = model.launch_count_total()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -273,13 +271,26 @@ def main():
     ev1.record(stream)
     idx, pose = model.wait()
     barrier()
-    t_w1 = time.time()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = model.launch_count_total() - launches0
-    gemm_ms, gemm_flops, gemm_launches = model.gemm_profile()
-    model.set_gemm_profile(False)
     units = N_HYP * (world if replicas else 1)  # hypotheses processed per step by all ranks
     value = args.steps * units / (dev_ms * 1e-3)
+
+    # ---- timed region 1b: the same K steps with every conv_gemm launch bracketed by CUDA events on
+    # the session stream (the brackets cost a few % of step time, so `value` comes from the clean pass)
+    model.set_gemm_profile(True)
+    model.gemm_profile()  # clear
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    ev3.record(stream)
+    model.wait()
+    barrier()
+    prof_ms = ev2.elapsed_time(ev3)
+    gemm_ms, gemm_flops, gemm_launches = model.gemm_profile()
+    model.set_gemm_profile(False)
 
     # ---- timed region 2: public call with host buffers (H2D + D2H + syncs inside)
     model.set_async(sw > 1)
@@ -329,7 +340,8 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM; all conv / linear layers)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src, "launches_timed": int(gemm_launches),
-                     "kernel_ms_per_step": gemm_ms / args.steps, "kernel_share_of_step": gemm_ms / dev_ms if dev_ms else None},
+                     "kernel_ms_per_step": gemm_ms / args.steps, "kernel_share_of_step": gemm_ms / prof_ms if prof_ms else None,
+                     "timing": "second pass of the same K steps with CUDA events around every conv_gemm launch"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import torch as _t

@@ -35,7 +35,12 @@ template <int BN, bool PAIR>
 struct Cfg {
   static constexpr int kCS = PAIR ? 2 : 1;
   static constexpr int kBTile = (BN * kGemmBlockK * 2) / kCS;  // weight bytes per CTA and tap
-  static constexpr int kTmemCols = 2 * BN;
+  // Accumulator stages in TMEM.  Wide tiles: 2 stages, the 8 epilogue warps split the columns of one
+  // tile.  Narrow tiles (short MMA time per tile): 4 stages, the two sets of 4 epilogue warps take
+  // alternate tiles, so that the fixed latency of an epilogue pass is overlapped across tiles.
+  static constexpr bool kAltTiles = BN <= 128;
+  static constexpr int kAccStages = kAltTiles ? 4 : 2;
+  static constexpr int kTmemCols = kAccStages * BN;
 };
 
 template <int BN, bool PAIR, bool PER_TAP>
@@ -49,12 +54,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const uint32_t b_base = a_base + p.na * p.a_bytes;        // [nb] weight stages
   const uint32_t stage_base = b_base + p.nb * p.b_stage_bytes;
   const uint32_t bar_base = stage_base + 8 * kStageBytesPerWarp;
-  // barrier layout (8 B each): full[8], empty[8], tfull[2], tempty[2], tmem ptr
+  // barrier layout (8 B each): full[8], empty[8], tfull[4], tempty[4], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxRing + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxRing + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxRing + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxRing + 4);
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxRing + 4 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxRing + 8);
   const uint32_t sched_base = bar_base + 256;  // kSchedMax x u32
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
       smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
@@ -69,10 +74,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       ptx::mbar_init(full_bar(s), PAIR ? 2 : 1);
       ptx::mbar_init(empty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < C::kAccStages; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      // one arrival per epilogue warp (PAIR: of both CTAs, on the leader's barrier)
-      ptx::mbar_init(tempty_bar(s), PAIR ? 16 : 8);
+      // one arrival per epilogue warp working on the tile (PAIR: of both CTAs, on the leader's barrier)
+      ptx::mbar_init(tempty_bar(s), (C::kAltTiles ? 4 : 8) * CS);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tm_a);
@@ -185,8 +190,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int n_entries = taps_cb * p.cblocks;
         uint32_t a_cur = a_lo0;
         for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
-          const int acc = it & 1;
-          const uint32_t acc_phase = (it >> 1) & 1;
+          const int acc = it % C::kAccStages;
+          const uint32_t acc_phase = (it / C::kAccStages) & 1;
           ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
@@ -230,8 +235,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       } else {
         for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
-          const int acc = it & 1;
-          const uint32_t acc_phase = (it >> 1) & 1;
+          const int acc = it % C::kAccStages;
+          const uint32_t acc_phase = (it / C::kAccStages) & 1;
           ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
@@ -293,15 +298,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // staging addresses (bytes): write = own row, read = rows i*8+sub
     const uint32_t wr_base = stg + lane * 128;
     const uint32_t rd_sw = static_cast<uint32_t>(sub & 7);
-    int it = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+    constexpr int kItStep = C::kAltTiles ? 2 : 1;     // narrow tiles: this warp set takes every other tile
+    constexpr int kColStep = C::kAltTiles ? 32 : 64;  // ... and all of its columns
+    for (int it = C::kAltTiles ? chunk_par : 0, tile = cluster_id + it * num_clusters; tile < total_tiles;
+         tile += kItStep * num_clusters, it += kItStep) {
       const int nt = tile % p.n_tiles;
       const int mt = (tile / p.n_tiles) * CS + crank;
       const int x0 = (mt % p.tiles_x) << p.bw_log2;
       const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
       const int n0 = (mt / (p.tiles_x * p.tiles_y)) << p.bn_log2;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % C::kAccStages;
+      const uint32_t acc_phase = (it / C::kAccStages) & 1;
       // per-lane bookkeeping for the 4 row groups (offsets in units of 8 halves = 16 bytes)
       uint32_t out_off[4], res_off[4], pp_off[4];
       uint32_t vmask = 0;
@@ -328,7 +335,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const float* bptr = p.bias + nt * BN + seg * 8;
       uint4* out16 = reinterpret_cast<uint4*>(p.out);
       const uint4* res16 = reinterpret_cast<const uint4*>(p.residual);
-      const int c_first = chunk_par * 32;
+      const int c_first = C::kAltTiles ? 0 : chunk_par * 32;
 
       // The residual rows of a chunk are fetched one chunk ahead (the first one before the wait on
       // the accumulator), so their DRAM/L2 latency overlaps the TMEM read and the staging.
@@ -348,7 +355,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t r[32];
       ptx::tmem_ld_32x32b_x32(taddr + c_first, r);
 #pragma unroll 1
-      for (int c0 = c_first; c0 < BN; c0 += 64) {
+      for (int c0 = c_first; c0 < BN; c0 += kColStep) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr + c0));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bptr + c0 + 4));
         ptx::tmem_ld_wait();
@@ -357,9 +364,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           ptx::st_shared_v4(wr_base + ((c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
         __syncwarp();
         uint4 res_nxt[4];
-        if (c0 + 64 < BN) {
-          ptx::tmem_ld_32x32b_x32(taddr + c0 + 64, r);
-          fetch_residual(res_nxt, c0 + 64);
+        if (c0 + kColStep < BN) {
+          ptx::tmem_ld_32x32b_x32(taddr + c0 + kColStep, r);
+          fetch_residual(res_nxt, c0 + kColStep);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -395,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if ((vmask >> i) & 1u) out16[out_off[i] + (c0 >> 3)] = u;
         }
         __syncwarp();
-        if (c0 + 64 < BN) {
+        if (c0 + kColStep < BN) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) res_cur[i] = res_nxt[i];
         }
