@@ -217,12 +217,17 @@ def main():
             dist.all_gather_into_tensor(dst, src)
 
     def step_resident():
+        if sw == 1 and not profiling[0]:
+            model.register_async(name, args.refine_itr)  # one CUDA-graph replay per Register
+            return
         model.sample_hypotheses(None, name)
         for _ in range(args.refine_itr):
             model.refine_step()
         model.score_features()
         gather()
         model.score_finish_async()
+
+    profiling = [False]
 
     def step_e2e():
         if sw == 1:
@@ -279,6 +284,7 @@ def main():
     # ---- timed region 1b: the same K steps with every conv_gemm launch bracketed by CUDA events on
     # the session stream (the brackets cost a few % of step time, so `value` comes from the clean pass)
     model.set_gemm_profile(True)
+    profiling[0] = True
     model.gemm_profile()  # clear
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -291,6 +297,7 @@ def main():
     prof_ms = ev2.elapsed_time(ev3)
     gemm_ms, gemm_flops, gemm_launches = model.gemm_profile()
     model.set_gemm_profile(False)
+    profiling[0] = False
 
     # ---- timed region 2: public call with host buffers (H2D + D2H + syncs inside)
     model.set_async(sw > 1)

@@ -257,6 +257,10 @@ class FoundationPose:
     def set_async(self, on: bool):
         capi.check(self._lib.fpb200_set_async(self._h, int(bool(on))))
 
+    def register_async(self, target_name: str, refine_itr: int = 1):
+        """Whole Register on the resident frame, enqueued without synchronising (see fpb200_register_async)."""
+        capi.check(self._lib.fpb200_register_async(self._h, target_name.encode(), int(refine_itr)))
+
     def score_finish_async(self):
         capi.check(self._lib.fpb200_score_finish_async(self._h))
 

@@ -16,29 +16,22 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One warp per row of 512 channels: lane l owns channels [8l, 8l+8) and [256 + 8l, 256 + 8l + 8),
-// i.e. two coalesced 16-byte loads per operand.
-__global__ void add_layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ y,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     __half* __restrict__ out, long long rows) {
-  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float v[16];
+// Loads this lane's 16 channels of one 512-channel row ([8l, 8l+8) and [256 + 8l, 256 + 8l + 8): two
+// coalesced 16-byte loads), normalises the row (LayerNorm, eps 1e-5, fp32 math) in place.
+__device__ __forceinline__ void load_row16(const __half* __restrict__ x, long long row, int lane, float (&v)[16]) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int c = h * 256 + lane * 8;
-    const uint4 a = *reinterpret_cast<const uint4*>(x + row * kDim + c);
-    const uint4 b = *reinterpret_cast<const uint4*>(y + row * kDim + c);
+    const uint4 a = *reinterpret_cast<const uint4*>(x + row * kDim + h * 256 + lane * 8);
     const __half2* ah = reinterpret_cast<const __half2*>(&a);
-    const __half2* bh = reinterpret_cast<const __half2*>(&b);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 fa = __half22float2(ah[e]), fb = __half22float2(bh[e]);
-      v[h * 8 + 2 * e] = fa.x + fb.x;
-      v[h * 8 + 2 * e + 1] = fa.y + fb.y;
+      const float2 fa = __half22float2(ah[e]);
+      v[h * 8 + 2 * e] = fa.x;
+      v[h * 8 + 2 * e + 1] = fa.y;
     }
   }
+}
+__device__ __forceinline__ void normalise_row16(float (&v)[16], const float (&g)[16], const float (&b)[16]) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += v[i];
@@ -51,18 +44,78 @@ __global__ void add_layernorm_kernel(const __half* __restrict__ x, const __half*
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.f / kDim) + 1e-5f);
 #pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (v[i] - mean) * rstd * g[i] + b[i];
+}
+__device__ __forceinline__ void load_affine16(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                              int lane, float (&g)[16], float (&b)[16]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      g[h * 8 + e] = gamma[h * 256 + lane * 8 + e];
+      b[h * 8 + e] = beta[h * 256 + lane * 8 + e];
+    }
+}
+
+// out = LayerNorm(x): one warp per row.  The residual sum x = a + f(a) was formed by the producing
+// GEMM's epilogue.
+__global__ void layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __half* __restrict__ out, long long rows) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[16], g[16], b[16];
+  load_row16(x, row, lane, v);
+  load_affine16(gamma, beta, lane, g, b);
+  normalise_row16(v, g, b);
+#pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int c = h * 256 + lane * 8;
     uint4 o;
     __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 g = *reinterpret_cast<const float2*>(gamma + c + 2 * e);
-      const float2 b = *reinterpret_cast<const float2*>(beta + c + 2 * e);
-      oh[e] = __floats2half2_rn((v[h * 8 + 2 * e] - mean) * rstd * g.x + b.x,
-                                (v[h * 8 + 2 * e + 1] - mean) * rstd * g.y + b.y);
+    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[h * 8 + 2 * e], v[h * 8 + 2 * e + 1]);
+    *reinterpret_cast<uint4*>(out + row * kDim + h * 256 + lane * 8) = o;
+  }
+}
+
+// mean over the 400 tokens of LayerNorm(x): the normalised tokens are only ever consumed through
+// their mean (pose heads), so they are never written.  One 512-thread CTA per hypothesis: warp w
+// normalises tokens w, w+16, ... and keeps a running sum in registers; the 16 partial sums are
+// combined through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(512)
+layernorm_mean_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float* __restrict__ out) {
+  __shared__ float part[16][kDim];
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[16], b[16], acc[16];
+  load_affine16(gamma, beta, lane, g, b);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  const long long row0 = static_cast<long long>(n) * kTok;
+  for (int t = warp; t < kTok; t += 32) {
+    float v0[16], v1[16];
+    const bool two = t + 16 < kTok;
+    load_row16(x, row0 + t, lane, v0);
+    if (two) load_row16(x, row0 + t + 16, lane, v1);
+    normalise_row16(v0, g, b);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] += v0[i];
+    if (two) {
+      normalise_row16(v1, g, b);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] += v1[i];
     }
-    *reinterpret_cast<uint4*>(out + row * kDim + c) = o;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[warp][h * 256 + lane * 8 + e] = acc[h * 8 + e];
+  __syncthreads();
+  {
+    float s = 0.f;
+#pragma unroll 8
+    for (int w = 0; w < 16; ++w) s += part[w][threadIdx.x];
+    out[static_cast<long long>(n) * kDim + threadIdx.x] = s * (1.f / kTok);
   }
 }
 
@@ -258,12 +311,18 @@ __global__ void refine_update_kernel(const float* __restrict__ mean_t, const flo
 
 }  // namespace
 
-void launch_add_layernorm(const __half* x, const __half* y, const float* gamma, const float* beta, __half* out,
-                          long long rows, cudaStream_t s) {
+void launch_layernorm(const __half* x, const float* gamma, const float* beta, __half* out, long long rows,
+                      cudaStream_t s) {
   if (rows <= 0) return;
   const int threads = 256;
   const long long blocks = (rows * 32 + threads - 1) / threads;
-  add_layernorm_kernel<<<(unsigned)blocks, threads, 0, s>>>(x, y, gamma, beta, out, rows);
+  layernorm_kernel<<<(unsigned)blocks, threads, 0, s>>>(x, gamma, beta, out, rows);
+}
+
+void launch_layernorm_mean(const __half* x, const float* gamma, const float* beta, float* out, int n,
+                           cudaStream_t s) {
+  if (n <= 0) return;
+  layernorm_mean_kernel<<<n, 512, 0, s>>>(x, gamma, beta, out);
 }
 
 void launch_token_mean(const __half* x, float* out, int n, cudaStream_t s) {

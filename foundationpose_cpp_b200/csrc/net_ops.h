@@ -11,10 +11,13 @@ const char* attention_init();
 // qkv: [n_hyp*400, qkv_ld] fp16 with Q | K | V blocks of 4 heads x 128; out: [n_hyp*400, out_ld].
 void launch_attention(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, cudaStream_t s);
 
-// out = LayerNorm(x + y) * gamma + beta over 512 channels, eps 1e-5 (post-LN of
-// nn.TransformerEncoderLayer).  x, y, out: [rows,512] fp16.
-void launch_add_layernorm(const __half* x, const __half* y, const float* gamma, const float* beta,
-                          __half* out, long long rows, cudaStream_t s);
+// out = LayerNorm(x) * gamma + beta over 512 channels, eps 1e-5 (post-LN of nn.TransformerEncoderLayer;
+// the residual sum x = a + sublayer(a) is formed by the producing GEMM's epilogue).  [rows,512] fp16.
+void launch_layernorm(const __half* x, const float* gamma, const float* beta, __half* out, long long rows,
+                      cudaStream_t s);
+// out[n,512] f32 = mean over the 400 tokens of LayerNorm(x[n,400,512]); the normalised tokens are not stored.
+void launch_layernorm_mean(const __half* x, const float* gamma, const float* beta, float* out, int n,
+                           cudaStream_t s);
 // mean over the 400 tokens: x [n,400,512] fp16 -> out [n,512] f32
 void launch_token_mean(const __half* x, float* out, int n, cudaStream_t s);
 // out[r,o] = sum_k in[r,k] * w[o,k] + b[o]   (fp32, small shapes)

@@ -190,12 +190,13 @@ void Network::add_backbone(Plan& p, int n) {
 
 namespace {
 ConvGemmDesc linear_desc(const __half* in, long long rows, int k, const __half* w, const float* b, int outs,
-                         __half* out, bool relu) {
+                         __half* out, bool relu, const __half* residual = nullptr) {
   ConvGemmDesc d;
   d.in = in; d.n_img = 1; d.planes = 1; d.in_h = 1; d.in_w = (int)rows; d.cin = k;
   d.out_h = 1; d.out_w = (int)rows; d.bw = 128; d.bh = 1; d.bn = 1;
   d.num_taps = 1;
   d.weight = w; d.cout = outs; d.bias = b; d.out = out; d.relu = relu;
+  d.residual = residual; d.res_ld = outs;
   return d;
 }
 }  // namespace
@@ -207,14 +208,15 @@ void Network::add_encoder_layer(Plan& p, int n, const std::string& h, float* mea
   add_gemm(p.steps, &p.flops, linear_desc(A.d0, rows, 512, W.f16(h + ".qkv.w", 1536, 512), W.f32(h + ".qkv.b", 1536), 1536, A.qkv, false));
   p.steps.push_back([&A, n](cudaStream_t s) { launch_attention(A.qkv, A.att, n, 1536, 512, s); });
   p.flops += 2.0 * n * 4 * 2 * 400.0 * 400.0 * 128.0;
-  add_gemm(p.steps, &p.flops, linear_desc(A.att, rows, 512, W.f16(h + ".out.w", 512, 512), W.f32(h + ".out.b", 512), 512, A.proj, false));
+  // post-LN encoder layer: the two residual sums are formed in the GEMM epilogues
+  add_gemm(p.steps, &p.flops, linear_desc(A.att, rows, 512, W.f16(h + ".out.w", 512, 512), W.f32(h + ".out.b", 512), 512, A.proj, false, A.d0));
   const float *g1 = W.f32(h + ".ln1.g", 512), *b1 = W.f32(h + ".ln1.b", 512);
-  p.steps.push_back([&A, rows, g1, b1](cudaStream_t s) { launch_add_layernorm(A.d0, A.proj, g1, b1, A.x1, rows, s); });
+  p.steps.push_back([&A, rows, g1, b1](cudaStream_t s) { launch_layernorm(A.proj, g1, b1, A.x1, rows, s); });
   add_gemm(p.steps, &p.flops, linear_desc(A.x1, rows, 512, W.f16(h + ".ff1.w", 512, 512), W.f32(h + ".ff1.b", 512), 512, A.ff1, true));
-  add_gemm(p.steps, &p.flops, linear_desc(A.ff1, rows, 512, W.f16(h + ".ff2.w", 512, 512), W.f32(h + ".ff2.b", 512), 512, A.ff2, false));
+  add_gemm(p.steps, &p.flops, linear_desc(A.ff1, rows, 512, W.f16(h + ".ff2.w", 512, 512), W.f32(h + ".ff2.b", 512), 512, A.ff2, false, A.x1));
   const float *g2 = W.f32(h + ".ln2.g", 512), *b2 = W.f32(h + ".ln2.b", 512);
-  p.steps.push_back([&A, rows, g2, b2](cudaStream_t s) { launch_add_layernorm(A.x1, A.ff2, g2, b2, A.x2, rows, s); });
-  p.steps.push_back([&A, n, mean_out](cudaStream_t s) { launch_token_mean(A.x2, mean_out, n, s); });
+  // the second LayerNorm's tokens are consumed only through their mean: fused, never stored
+  p.steps.push_back([&A, n, g2, b2, mean_out](cudaStream_t s) { launch_layernorm_mean(A.ff2, g2, b2, mean_out, n, s); });
   p.flops += 2.0 * n * 512 * 3;  // Linear(512,3) on the token mean
 }
 

@@ -606,6 +606,32 @@ int fpb200_register(fpb200_session* s, const uint8_t* rgb, const float* depth, c
   });
 }
 
+int fpb200_register_async(fpb200_session* s, const char* target_name, int refine_itr) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    FPB_REQUIRE(s->opt.shard_world == 1, "fpb200_register_async needs shard_world == 1; sharded sessions use the stage API");
+    if (!s->uploaded) return fail(FPB200_ERR_STATE, "fpb200_upload must be called first");
+    MeshEntry* mesh = s->find_mesh(target_name);
+    FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
+    FPB_REQUIRE(refine_itr >= 0, "refine_itr must be >= 0");
+    s->launches = 0;
+    FPB_CUDA(cudaMemsetAsync(s->status.p, 0, sizeof(int), s->stream));
+    s->cur_mesh = mesh;
+    s->set_shard(std::min(kGridPoses, s->opt.max_hyps));
+    char key[160];
+    snprintf(key, sizeof(key), "register_async:%d:%dx%d:%p", refine_itr, s->img_h, s->img_w, (void*)mesh);
+    run_maybe_graphed(s, key, [&]() {
+      do_sample(s, mesh);
+      for (int i = 0; i < refine_itr; ++i) do_refine_step(s);
+      do_score_features(s);
+      do_score_finish(s);
+      enqueue_result_read(s);
+    });
+    s->features_ready = true;
+    return FPB200_OK;
+  });
+}
+
 int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w, const float hyp_pose[16],
                  const char* target_name, int refine_itr, float out_pose[16]) {
   return guard([&]() -> int {

@@ -72,6 +72,12 @@ void fpb200_destroy(fpb200_session* s);
 /* Base6DofDetectionModel::Register (fp/src/foundationpose.cpp:181-228). */
 int fpb200_register(fpb200_session* s, const uint8_t* rgb, const float* depth, const uint8_t* mask,
                     int h, int w, const char* target_name, int refine_itr, float out_pose[16]);
+/* Register on the frame (and mask) ALREADY resident in device memory (fpb200_upload +
+ * fpb200_sample_hypotheses with a mask were called before): enqueues sampler -> refine x itr ->
+ * score -> argmax on the session stream (CUDA-graph replay after the second call) and returns without
+ * synchronising; fpb200_wait delivers the pose.  Same result as fpb200_register on the same frame. */
+int fpb200_register_async(fpb200_session* s, const char* target_name, int refine_itr);
+
 /* Base6DofDetectionModel::Track (fp/src/foundationpose.cpp:230-265). */
 int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w,
                  const float hyp_pose[16], const char* target_name, int refine_itr,

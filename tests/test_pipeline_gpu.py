@@ -192,6 +192,20 @@ def test_cuda_graph_replay_matches_eager(env):
     assert ok and np.isfinite(p2).all()
 
 
+def test_register_async_matches_register(env):
+    """fpb200_register_async (frame already resident, no host sync until wait) == the public Register."""
+    m = env["model"]
+    ok, ref = m.Register(env["rgb"], env["depth"], env["mask"], "mustard_proxy", refine_itr=1)
+    assert ok
+    m.upload(env["rgb"], env["depth"])
+    m.sample_hypotheses(env["mask"], "mustard_proxy")
+    for _ in range(3):  # eager, capture, replay
+        m.register_async("mustard_proxy", 1)
+        idx, pose = m.wait()
+        assert np.array_equal(pose, ref)
+        assert 0 <= idx < 252
+
+
 def test_infer_core_boundary(tmp_path):
     """The BaseInferCore-shaped entry points on the reference's own blob layout (f32 NHWC [n,160,160,6])."""
     import ctypes as C
