@@ -51,30 +51,40 @@ __device__ __forceinline__ void load_affine16(const float* __restrict__ gamma, c
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      g[h * 8 + e] = gamma[h * 256 + lane * 8 + e];
-      b[h * 8 + e] = beta[h * 256 + lane * 8 + e];
+    for (int e = 0; e < 2; ++e) {
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + h * 256 + lane * 8 + 4 * e));
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(beta + h * 256 + lane * 8 + 4 * e));
+      g[h * 8 + 4 * e + 0] = gv.x; g[h * 8 + 4 * e + 1] = gv.y; g[h * 8 + 4 * e + 2] = gv.z; g[h * 8 + 4 * e + 3] = gv.w;
+      b[h * 8 + 4 * e + 0] = bv.x; b[h * 8 + 4 * e + 1] = bv.y; b[h * 8 + 4 * e + 2] = bv.z; b[h * 8 + 4 * e + 3] = bv.w;
     }
 }
 
-// out = LayerNorm(x): one warp per row.  The residual sum x = a + f(a) was formed by the producing
-// GEMM's epilogue.
-__global__ void layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, __half* __restrict__ out, long long rows) {
-  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+// out = LayerNorm(x): one warp per kLnRows consecutive rows (all loads issued before the first
+// reduction).  The residual sum x = a + f(a) was formed by the producing GEMM's epilogue.
+constexpr int kLnRows = 4;
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, __half* __restrict__ out, long long rows) {
+  const long long row0 = ((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * kLnRows;
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float v[16], g[16], b[16];
-  load_row16(x, row, lane, v);
+  if (row0 >= rows) return;
+  float v[kLnRows][16], g[16], b[16];
+#pragma unroll
+  for (int r = 0; r < kLnRows; ++r)
+    if (row0 + r < rows) load_row16(x, row0 + r, lane, v[r]);
   load_affine16(gamma, beta, lane, g, b);
-  normalise_row16(v, g, b);
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
+  for (int r = 0; r < kLnRows; ++r) {
+    if (row0 + r >= rows) break;
+    normalise_row16(v[r], g, b);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[h * 8 + 2 * e], v[h * 8 + 2 * e + 1]);
-    *reinterpret_cast<uint4*>(out + row * kDim + h * 256 + lane * 8) = o;
+    for (int h = 0; h < 2; ++h) {
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[r][h * 8 + 2 * e], v[r][h * 8 + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(out + (row0 + r) * kDim + h * 256 + lane * 8) = o;
+    }
   }
 }
 
@@ -315,7 +325,8 @@ void launch_layernorm(const __half* x, const float* gamma, const float* beta, __
                       cudaStream_t s) {
   if (rows <= 0) return;
   const int threads = 256;
-  const long long blocks = (rows * 32 + threads - 1) / threads;
+  const long long warps = (rows + kLnRows - 1) / kLnRows;
+  const long long blocks = (warps * 32 + threads - 1) / threads;
   layernorm_kernel<<<(unsigned)blocks, threads, 0, s>>>(x, gamma, beta, out, rows);
 }
 

@@ -216,3 +216,64 @@ def write_seeded(dirpath: str, refiner_seed: int = 2, scorer_seed: int = 3):
     export_refiner(rp, seeded_state_dict(KIND_REFINER, refiner_seed))
     export_scorer(sp, seeded_state_dict(KIND_SCORER, scorer_seed))
     return rp, sp
+
+
+# ----------------------------------------------------------------------------- importers
+# conv layers in forward order; ONNX exporters that fold BatchNorm leave the convolutions with
+# anonymous initializer names ("onnx::Conv_123"), so they are matched by position
+_CONV_ORDER = (["backbone.encodeA.0.conv", "backbone.encodeA.1.conv"] +
+               [f"backbone.encodeA.{i}.conv{c}" for i in (2, 3) for c in (1, 2)] +
+               [f"backbone.encodeAB.{i}.conv{c}" for i in (0, 1) for c in (1, 2)] +
+               ["backbone.encodeAB.2.conv"] +
+               [f"backbone.encodeAB.{i}.conv{c}" for i in (3, 4) for c in (1, 2)])
+
+
+def load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
+    """PyTorch checkpoint (.pth / .pt) -> flat state_dict with the upstream parameter names.
+    Accepts a bare state_dict or the usual wrappers ({'model': ...}, {'state_dict': ...}) and strips a
+    DataParallel 'module.' prefix."""
+    obj = torch.load(path, map_location="cpu", weights_only=True)
+    for key in ("model", "state_dict", "model_state_dict"):
+        if isinstance(obj, dict) and key in obj and isinstance(obj[key], dict):
+            obj = obj[key]
+    if not isinstance(obj, dict) or not all(isinstance(v, torch.Tensor) for v in obj.values()):
+        raise ValueError(f"{path}: not a state_dict")
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in obj.items()}
+
+
+def onnx_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """ONNX model (the refiner_hwc.onnx / scorer_hwc.onnx the reference feeds to trtexec,
+    tools/cvt_onnx2trt.bash:3-15) -> state_dict with the upstream parameter names.
+
+    Named initializers are taken as they are.  Convolutions whose weights lost their names because the
+    exporter folded BatchNorm into them are matched BY POSITION: distinct Conv weight initializers in
+    graph order = the 15 backbone convolutions in forward order (the siamese encodeA branch shares one
+    set of weights, so its second appearance is skipped).  Anything else that is missing is reported
+    by the exporter as a KeyError naming the parameter."""
+    from . import onnx_reader
+    inits, nodes = onnx_reader.read_onnx(path)
+    sd = {k: torch.from_numpy(v) for k, v in inits.items() if v.dtype in (np.float32, np.float16)}
+    if _CONV_ORDER[0] + ".weight" not in sd:
+        seen, convs = set(), []
+        for op, ins, _ in nodes:
+            if op == "Conv" and len(ins) >= 2 and ins[1] in inits and ins[1] not in seen:
+                seen.add(ins[1])
+                convs.append(ins)
+        if len(convs) != len(_CONV_ORDER):
+            raise ValueError(f"{path}: expected {len(_CONV_ORDER)} distinct convolutions, found {len(convs)}")
+        for name, ins in zip(_CONV_ORDER, convs):
+            w = torch.from_numpy(inits[ins[1]]).float()
+            sd[name + ".weight"] = w
+            sd[name + ".bias"] = (torch.from_numpy(inits[ins[2]]).float() if len(ins) > 2 and ins[2] in inits
+                                  else torch.zeros(w.shape[0]))
+    if "backbone.pe" not in sd:
+        sd["backbone.pe"] = positional_table()  # a pure function of the architecture, not a trained tensor
+    return {k: v.float() for k, v in sd.items()}
+
+
+def import_weights(src: str, dst: str, kind: int) -> None:
+    """src: .pth/.pt checkpoint or .onnx model of the refine (kind 0) / score (kind 1) network ->
+    dst: flat FPB2W file for fpb200_create."""
+    sd = onnx_state_dict(src) if src.lower().endswith(".onnx") else load_checkpoint(src)
+    tensors = refiner_tensors(sd) if kind == KIND_REFINER else scorer_tensors(sd)
+    write_weight_file(dst, kind, tensors)

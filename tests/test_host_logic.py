@@ -166,3 +166,52 @@ def test_obj_mesh_loader_roundtrip(tmp_path):
     open(q, "w").write("v 0 0 0\nv 1 0 0\nv 1 1 0\nf 1 2 3\n")
     with pytest.raises(ValueError):
         mesh_loader.load_obj(q)
+
+
+def test_weight_importers_pth_and_onnx(tmp_path):
+    """a .pth checkpoint and an ONNX model (named initializers, and the BN-folded form
+    with anonymous Conv weights matched by position) produce the same FPB2W file as the exporter."""
+    import numpy as np
+    import torch
+    from foundationpose_cpp_b200 import onnx_reader, weights
+    for kind in (weights.KIND_REFINER, weights.KIND_SCORER):
+        sd = weights.seeded_state_dict(kind, 11 + kind)
+        ref = tmp_path / f"ref{kind}.fpb2w"
+        (weights.export_refiner if kind == weights.KIND_REFINER else weights.export_scorer)(str(ref), sd)
+        want = weights.read_weight_file(str(ref))
+        # 1) .pth, wrapped and with a DataParallel prefix
+        pth = tmp_path / f"k{kind}.pth"
+        torch.save({"model": {"module." + k: v for k, v in sd.items()}}, pth)
+        out = tmp_path / f"pth{kind}.fpb2w"
+        weights.import_weights(str(pth), str(out), kind)
+        got = weights.read_weight_file(str(out))
+        assert got.keys() == want.keys() and all(np.array_equal(got[k], want[k]) for k in want)
+        # 2) ONNX with named initializers (fp16 and fp32 tensors, raw_data encoding)
+        onx = tmp_path / f"k{kind}.onnx"
+        onnx_reader.write_onnx(str(onx), {k: v.numpy() for k, v in sd.items()})
+        inits, _ = onnx_reader.read_onnx(str(onx))
+        assert all(np.array_equal(inits[k], sd[k].numpy()) for k in sd)
+        out = tmp_path / f"onnx{kind}.fpb2w"
+        weights.import_weights(str(onx), str(out), kind)
+        got = weights.read_weight_file(str(out))
+        assert all(np.array_equal(got[k], want[k]) for k in want)
+        # 3) ONNX as exporters write it in eval mode: BN folded, Conv weights anonymous, siamese branch twice
+        folded, nodes, n = {}, [], 0
+        for name in weights._CONV_ORDER:
+            bn = name.replace(".conv", ".bn") if name.endswith(".conv") else name.replace("conv", "bn")
+            w, b = weights._fold(sd, name, bn)
+            folded[f"onnx::Conv_{n}"], folded[f"onnx::Conv_{n + 1}"] = w.numpy(), b.numpy()
+            nodes.append(("Conv", [f"x{n}", f"onnx::Conv_{n}", f"onnx::Conv_{n + 1}"], [f"y{n}"]))
+            if "encodeA." in name:  # second siamese branch reuses the initializers
+                nodes.append(("Conv", [f"xb{n}", f"onnx::Conv_{n}", f"onnx::Conv_{n + 1}"], [f"yb{n}"]))
+            n += 2
+        for k, v in sd.items():
+            if not k.startswith("backbone.encode"):
+                folded[k] = v.numpy()
+        onx2 = tmp_path / f"folded{kind}.onnx"
+        onnx_reader.write_onnx(str(onx2), folded, nodes)
+        out = tmp_path / f"folded{kind}.fpb2w"
+        weights.import_weights(str(onx2), str(out), kind)
+        got = weights.read_weight_file(str(out))
+        for k in want:
+            np.testing.assert_allclose(got[k].astype(np.float32), want[k].astype(np.float32), rtol=2e-3, atol=1e-6)
