@@ -42,3 +42,26 @@ def test_depth_kernels_match_reference():
 
 def test_argmax_matches_thrust_max_element():
     assert O.argmax_first(G["scores"]) == int(G["ref_argmax"]) == 1  # first of the two equal maxima
+
+
+def test_network_oracle_reproduces_committed_outputs():
+    """tests/golden/nets_golden.npz (make_nets_golden.py): the fp32 PyTorch oracle of the refine / score
+    networks on seeded weights and inputs.  Pins the oracle against drift; the CUDA path is checked
+    against the same file in test_pipeline_gpu.py."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import fp_helpers as helpers
+    import make_nets_golden as mk
+    from oracle import nets
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nets_golden.npz"))
+    a, b = mk.golden_inputs()
+    assert abs(float(a.sum() + 2 * b.sum()) - float(g["input_checksum"])) < 1e-3 * abs(float(g["input_checksum"]))
+    refiner, scorer = helpers.seeded_nets()
+    n = 2  # two of the three hypotheses keep the CPU suite short; the scorer needs all of them (cross-attention)
+    with torch.no_grad():
+        trans, rot = refiner(nets.nhwc_to_inputs(torch.from_numpy(a[:n])), nets.nhwc_to_inputs(torch.from_numpy(b[:n])))
+        scores = scorer(nets.nhwc_to_inputs(torch.from_numpy(a)), nets.nhwc_to_inputs(torch.from_numpy(b)))
+    np.testing.assert_allclose(trans.numpy(), g["trans"][:n], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(rot.numpy(), g["rot"][:n], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(scores.numpy().reshape(-1), g["scores"], rtol=1e-3, atol=1e-5)

@@ -9,6 +9,8 @@ Tolerances (stated per test):
 """
 import math
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -204,6 +206,37 @@ def test_register_async_matches_register(env):
         idx, pose = m.wait()
         assert np.array_equal(pose, ref)
         assert 0 <= idx < 252
+
+
+def test_networks_match_committed_golden_outputs(tmp_path):
+    """CUDA refine / score networks (through the infer-core C ABI) against tests/golden/nets_golden.npz,
+    the committed outputs of the fp32 oracle on seeded weights and inputs."""
+    import ctypes as C
+    import sys
+    from foundationpose_cpp_b200 import capi
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_nets_golden as mk
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nets_golden.npz"))
+    a, b = mk.golden_inputs()
+    n = a.shape[0]
+    rp, sp = helpers.write_seeded_weights(str(tmp_path))
+    lib = capi.lib()
+    ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    core = C.c_void_p()
+    capi.check(lib.fpb200_infer_create(rp.encode(), 0, 8, 0, C.byref(core)))
+    trans, rot = torch.zeros(n, 3, device="cuda"), torch.zeros(n, 3, device="cuda")
+    capi.check(lib.fpb200_infer_refiner(core, C.c_void_p(ad.data_ptr()), C.c_void_p(bd.data_ptr()), n,
+                                        C.c_void_p(trans.data_ptr()), C.c_void_p(rot.data_ptr())))
+    lib.fpb200_infer_destroy(core)
+    _net_close(trans.cpu().numpy(), g["trans"], "golden trans")
+    _net_close(rot.cpu().numpy(), g["rot"], "golden rot")
+    core = C.c_void_p()
+    capi.check(lib.fpb200_infer_create(sp.encode(), 1, 8, 0, C.byref(core)))
+    scores = torch.zeros(n, device="cuda")
+    capi.check(lib.fpb200_infer_scorer(core, C.c_void_p(ad.data_ptr()), C.c_void_p(bd.data_ptr()), n,
+                                       C.c_void_p(scores.data_ptr())))
+    lib.fpb200_infer_destroy(core)
+    np.testing.assert_allclose(scores.cpu().numpy(), g["scores"], atol=5e-3)
 
 
 def test_infer_core_boundary(tmp_path):
