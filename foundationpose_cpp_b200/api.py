@@ -175,6 +175,19 @@ class FoundationPose:
                                               target_name.encode(), int(refine_itr), _fptr(out)))
         return ok, (out.reshape(4, 4).T.copy() if ok else None)
 
+    def track_async(self, rgb, depth, hyp_pose_in_mesh, target_name: str, refine_itr: int = 1):
+        """Enqueue one Track without waiting (fpb200_track_async); rgb / depth must be C-contiguous arrays
+        of the right dtype that stay alive until track_wait."""
+        hyp = np.ascontiguousarray(np.asarray(hyp_pose_in_mesh, np.float32).T)
+        h, w = depth.shape
+        capi.check(self._lib.fpb200_track_async(self._h, _fptr(rgb), _fptr(depth), h, w, _fptr(hyp),
+                                                target_name.encode(), int(refine_itr)))
+
+    def track_wait(self):
+        out = np.zeros(16, np.float32)
+        capi.check(self._lib.fpb200_track_wait(self._h, _fptr(out)))
+        return out.reshape(4, 4).T.copy()
+
     # ---- stage API (tests, multi-GPU) ----------------------------------------------------
     def upload(self, rgb, depth):
         rgb, depth, _ = self._check_images(rgb, depth)

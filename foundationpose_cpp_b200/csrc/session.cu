@@ -151,6 +151,7 @@ struct MeshEntry {
 
 struct HostResult {
   float pose[16];
+  float hyp[16];  // staging of the Track hypothesis
   int best_index;
   int status;
 };
@@ -632,16 +633,17 @@ int fpb200_register_async(fpb200_session* s, const char* target_name, int refine
   });
 }
 
-int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w, const float hyp_pose[16],
-                 const char* target_name, int refine_itr, float out_pose[16]) {
+int fpb200_track_async(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w,
+                       const float hyp_pose[16], const char* target_name, int refine_itr) {
   return guard([&]() -> int {
-    FPB_REQUIRE(s && out_pose && hyp_pose, "null session / pose");
+    FPB_REQUIRE(s && hyp_pose, "null session / pose");
     MeshEntry* mesh = s->find_mesh(target_name);
     FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
     FPB_REQUIRE(refine_itr >= 0, "refine_itr must be >= 0");
     reset_call(s);
     do_upload(s, rgb, depth, h, w);
-    FPB_CUDA(cudaMemcpyAsync(s->poses.p, hyp_pose, sizeof(float) * 16, cudaMemcpyHostToDevice, s->stream));
+    memcpy(s->host_result->hyp, hyp_pose, sizeof(float) * 16);  // pinned staging: the caller's array may go away
+    FPB_CUDA(cudaMemcpyAsync(s->poses.p, s->host_result->hyp, sizeof(float) * 16, cudaMemcpyHostToDevice, s->stream));
     s->cur_mesh = mesh;
     s->n_hyp = 1; s->lo = 0; s->hi = 1; s->shard_cap = 1; s->features_ready = false;
     char key[160];
@@ -653,10 +655,24 @@ int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int 
       s->mark(4);
       FPB_CUDA(cudaMemcpyAsync(s->host_result->pose, s->poses.p, sizeof(float) * 16, cudaMemcpyDeviceToHost, s->stream));
     });
+    return FPB200_OK;
+  });
+}
+
+int fpb200_track_wait(fpb200_session* s, float out_pose[16]) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && out_pose, "null session / output");
     FPB_CUDA(cudaStreamSynchronize(s->stream));
     memcpy(out_pose, s->host_result->pose, sizeof(float) * 16);
     return FPB200_OK;
   });
+}
+
+int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w, const float hyp_pose[16],
+                 const char* target_name, int refine_itr, float out_pose[16]) {
+  if (!out_pose) return fail(FPB200_ERR_INVALID, "null output");
+  const int rc = fpb200_track_async(s, rgb, depth, h, w, hyp_pose, target_name, refine_itr);
+  return rc != FPB200_OK ? rc : fpb200_track_wait(s, out_pose);
 }
 
 int fpb200_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w) {

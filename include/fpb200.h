@@ -82,6 +82,14 @@ int fpb200_register_async(fpb200_session* s, const char* target_name, int refine
 int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w,
                  const float hyp_pose[16], const char* target_name, int refine_itr,
                  float out_pose[16]);
+/* Track split in two for callers that pipeline several sessions (one per object / camera) from one
+ * host thread, the role EasyDeploy's async pipeline plays around the reference
+ * (deploy_core/async_pipeline.h:78-242): fpb200_track_async enqueues upload + refine + read-back on the
+ * session stream and returns; fpb200_track_wait blocks until the pose is there.  rgb / depth must stay
+ * valid until the wait returns (pinned host memory makes the upload truly asynchronous). */
+int fpb200_track_async(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w,
+                       const float hyp_pose[16], const char* target_name, int refine_itr);
+int fpb200_track_wait(fpb200_session* s, float out_pose[16]);
 
 /* ---- stage-level entry points (the reference's private seams), used by tests / multi-GPU ---- */
 

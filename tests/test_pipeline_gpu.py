@@ -208,6 +208,18 @@ def test_register_async_matches_register(env):
         assert 0 <= idx < 252
 
 
+def test_track_async_matches_track(env):
+    """fpb200_track_async + fpb200_track_wait (pipelining several sessions from one thread) == Track."""
+    m = env["model"]
+    hyp = synth.perturb_pose(env["gt"], 5.0, 0.01, 3)
+    ok, ref = m.Track(env["rgb"], env["depth"], hyp, "mustard_proxy", refine_itr=2)
+    assert ok
+    rgb, depth = np.ascontiguousarray(env["rgb"]), np.ascontiguousarray(env["depth"], np.float32)
+    for _ in range(3):
+        m.track_async(rgb, depth, hyp, "mustard_proxy", 2)
+        assert np.array_equal(m.track_wait(), ref)
+
+
 def test_networks_match_committed_golden_outputs(tmp_path):
     """CUDA refine / score networks (through the infer-core C ABI) against tests/golden/nets_golden.npz,
     the committed outputs of the fp32 oracle on seeded weights and inputs."""
