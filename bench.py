@@ -78,7 +78,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.rows:
             if ts < t0 - 0.05 or ts > t1 + 0.05:
@@ -87,14 +87,16 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx = float(f[1])
+                pw.append(float(f[2]))
             except Exception:
                 continue
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         sm.sort()
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None}
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)

@@ -82,3 +82,19 @@ def debug_attention(qkv_ptr: int, out_ptr: int, n_hyp: int, repeat: int = 0) -> 
     check(lib().fpb200_debug_attention(C.c_void_p(qkv_ptr), C.c_void_p(out_ptr), C.c_int(n_hyp), C.c_int(repeat),
                                        C.byref(ms)))
     return ms.value
+
+
+def debug_small_linear(in_ptr: int, w_ptr: int, b_ptr: int, out_ptr: int, rows: int, k: int, outs: int,
+                       repeat: int = 0) -> float:
+    ms = C.c_float(0)
+    check(lib().fpb200_debug_small_linear(C.c_void_p(in_ptr), C.c_void_p(w_ptr), C.c_void_p(b_ptr or None),
+                                          C.c_void_p(out_ptr), C.c_int(rows), C.c_int(k), C.c_int(outs),
+                                          C.c_int(repeat), C.byref(ms)))
+    return ms.value
+
+
+def debug_cross_attention(qkv_ptr: int, out_ptr: int, n: int, repeat: int = 0) -> float:
+    ms = C.c_float(0)
+    check(lib().fpb200_debug_cross_attention(C.c_void_p(qkv_ptr), C.c_void_p(out_ptr), C.c_int(n), C.c_int(repeat),
+                                             C.byref(ms)))
+    return ms.value

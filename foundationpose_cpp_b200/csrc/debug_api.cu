@@ -2,6 +2,8 @@
 // kernel of the hot path on caller-provided DEVICE pointers.  Declared in include/fpb200.h.
 #include <cuda_runtime.h>
 
+#include <stdexcept>
+
 #include "../../include/fpb200.h"
 #include "common.h"
 #include "conv_gemm.h"
@@ -92,6 +94,47 @@ extern "C" int fpb200_debug_attention(const void* qkv, void* out, int n_hyp, int
   } catch (const std::exception& e) {
     return fail(FPB200_ERR_CUDA, "%s", e.what());
   }
+}
+
+namespace {
+template <typename F>
+int timed_launches(F&& launch, int repeat, float* ms_out) {
+  try {
+    cudaEvent_t e0, e1;
+    FPB_CUDA(cudaEventCreate(&e0));
+    FPB_CUDA(cudaEventCreate(&e1));
+    launch();
+    FPB_CUDA(cudaGetLastError());
+    FPB_CUDA(cudaEventRecord(e0, 0));
+    for (int i = 0; i < repeat; ++i) launch();
+    FPB_CUDA(cudaEventRecord(e1, 0));
+    FPB_CUDA(cudaDeviceSynchronize());
+    float ms = 0.f;
+    FPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = repeat > 0 ? ms / repeat : 0.f;
+    return FPB200_OK;
+  } catch (const std::invalid_argument& e) {
+    return fail(FPB200_ERR_INVALID, "%s", e.what());
+  } catch (const std::exception& e) {
+    return fail(FPB200_ERR_CUDA, "%s", e.what());
+  }
+}
+}  // namespace
+
+extern "C" int fpb200_debug_small_linear(const float* in, const float* w, const float* b, float* out, int rows, int k,
+                                         int outs, int repeat, float* ms_out) {
+  return timed_launches([&]() { launch_small_linear(in, w, b, out, rows, k, outs, 0); }, repeat, ms_out);
+}
+
+extern "C" int fpb200_debug_cross_attention(const float* qkv, float* out, int n, int repeat, float* ms_out) {
+  return timed_launches([&]() { launch_cross_attention(qkv, out, n, 0); }, repeat, ms_out);
+}
+
+extern "C" int fpb200_debug_attention_phases(unsigned long long out[22]) {
+  return attention_phase_clocks(out) ? FPB200_OK
+                                     : fail(FPB200_ERR_STATE, "set FPB200_ATTN_PHASES=1 before the first attention launch");
 }
 
 extern "C" const char* fpb200_last_error(void) { return last_error().c_str(); }

@@ -2,6 +2,7 @@
 #include "net_ops.h"
 
 #include <cfloat>
+#include <stdexcept>
 
 namespace fpb {
 
@@ -153,75 +154,168 @@ token_mean_kernel(const __half* __restrict__ x, float* __restrict__ out) {
   }
 }
 
-// Block = 8 rows x 8 warps; each warp produces outputs o = warp, warp+8, ... of its column slab
-// for all 8 rows, reading each weight row once (coalesced across lanes).
-constexpr int kSLRows = 8;
-__global__ void small_linear_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                    const float* __restrict__ b, float* __restrict__ out, int rows, int k,
-                                    int outs) {
-  extern __shared__ float s_in[];  // [kSLRows][k]
-  const int r0 = blockIdx.x * kSLRows;
-  for (int i = threadIdx.x; i < kSLRows * k; i += blockDim.x) {
-    const int r = i / k;
-    s_in[i] = (r0 + r < rows) ? in[static_cast<long long>(r0 + r) * k + (i - r * k)] : 0.f;
-  }
+// out[rows, outs] = in[rows, k] * w[outs, k]^T + b, fp32 (the scorer tail after the token mean: 252 rows).
+// 32 x 32 output tile per 256-thread CTA (so a 252 x 512 product spreads over 128 CTAs), K in chunks
+// of 32 through double-buffered shared memory; thread (ty, tx) owns row ty and outputs tx, tx+8, tx+16,
+// tx+24 and walks k four at a time with 16-byte shared loads (row pitch 36 floats: the eight lanes of
+// a quarter-warp hit disjoint banks, the row operand is a broadcast).  Sums run in ascending k.
+constexpr int kSGTile = 32, kSGChunk = 32, kSGPitch = kSGChunk + 4;
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b,
+                    float* __restrict__ out, int rows, int k, int outs) {
+  __shared__ __align__(16) float s_a[2][kSGTile * kSGPitch];
+  __shared__ __align__(16) float s_w[2][kSGTile * kSGPitch];
+  const int r0 = blockIdx.x * kSGTile, o0 = blockIdx.y * kSGTile;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  // loader mapping: thread -> (tile row lr, 16-byte column lc) of both tiles
+  const int lr = threadIdx.x >> 3, lc = (threadIdx.x & 7) * 4;
+  const bool a_ok = r0 + lr < rows, w_ok = o0 + lr < outs;
+  const float* a_src = in + static_cast<long long>(a_ok ? r0 + lr : 0) * k + lc;
+  const float* w_src = w + static_cast<long long>(w_ok ? o0 + lr : 0) * k + lc;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch = [&](int kc, float4& av, float4& wv) {
+    const bool in_k = kc + lc < k;  // k is a multiple of 4 (checked by the launcher)
+    av = (a_ok && in_k) ? __ldg(reinterpret_cast<const float4*>(a_src + kc)) : zero4;
+    wv = (w_ok && in_k) ? __ldg(reinterpret_cast<const float4*>(w_src + kc)) : zero4;
+  };
+  float4 av, wv;
+  fetch(0, av, wv);
+  *reinterpret_cast<float4*>(&s_a[0][lr * kSGPitch + lc]) = av;
+  *reinterpret_cast<float4*>(&s_w[0][lr * kSGPitch + lc]) = wv;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int o_begin = blockIdx.y * 64, o_end = min(outs, o_begin + 64);
-  for (int o = o_begin + warp; o < o_end; o += nw) {
-    float acc[kSLRows];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int n_chunks = (k + kSGChunk - 1) / kSGChunk;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < n_chunks) fetch((c + 1) * kSGChunk, av, wv);
+    const float* pa = &s_a[cur][ty * kSGPitch];
+    const float* pw = &s_w[cur][tx * kSGPitch];
 #pragma unroll
-    for (int r = 0; r < kSLRows; ++r) acc[r] = 0.f;
-    const float* wr = w + static_cast<long long>(o) * k;
-    for (int c = lane; c < k; c += 32) {
-      const float wv = wr[c];
+    for (int kk = 0; kk < kSGChunk; kk += 4) {
+      const float4 a4 = *reinterpret_cast<const float4*>(pa + kk);
 #pragma unroll
-      for (int r = 0; r < kSLRows; ++r) acc[r] += wv * s_in[r * k + c];
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = *reinterpret_cast<const float4*>(pw + j * 8 * kSGPitch + kk);
+        acc[j] = fmaf(a4.x, w4.x, acc[j]);
+        acc[j] = fmaf(a4.y, w4.y, acc[j]);
+        acc[j] = fmaf(a4.z, w4.z, acc[j]);
+        acc[j] = fmaf(a4.w, w4.w, acc[j]);
+      }
     }
+    if (c + 1 < n_chunks) {
+      *reinterpret_cast<float4*>(&s_a[cur ^ 1][lr * kSGPitch + lc]) = av;
+      *reinterpret_cast<float4*>(&s_w[cur ^ 1][lr * kSGPitch + lc]) = wv;
+    }
+    __syncthreads();
+  }
+  if (r0 + ty < rows) {
 #pragma unroll
-    for (int r = 0; r < kSLRows; ++r) {
-      const float v = warp_sum(acc[r]);
-      if (lane == 0 && r0 + r < rows) out[static_cast<long long>(r0 + r) * outs + o] = v + (b ? b[o] : 0.f);
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + tx + 8 * j;
+      if (o < outs) out[static_cast<long long>(r0 + ty) * outs + o] = acc[j] + (b ? b[o] : 0.f);
     }
   }
 }
 
-// One warp per (query, head): 128-d dot products with every key, softmax, weighted sum of V.
-__global__ void cross_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n) {
-  extern __shared__ float s_p[];  // [warps][n]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int item = blockIdx.x * nw + warp;
-  if (item >= n * 4) return;
-  const int qi = item >> 2, head = item & 3;
-  float* p = s_p + warp * n;
-  const float4 q = *reinterpret_cast<const float4*>(qkv + static_cast<long long>(qi) * 1536 + head * 128 + lane * 4);
+// out[r] = in[r, :] . w + b: one warp per row (the scorer's final Linear(512, 1)).
+__global__ void row_dot_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                               const float* __restrict__ b, float* __restrict__ out, int rows, int k) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float acc = 0.f;
+  for (int c = lane; c < k; c += 32) acc = fmaf(in[static_cast<long long>(r) * k + c], w[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc + (b ? b[0] : 0.f);
+}
+
+// Cross-hypothesis attention of the scorer tail: n tokens (one per hypothesis), 4 heads x 128 dims,
+// fp32.  One CTA = 8 queries (one per warp) of one head.  Keys, then values, stream through shared
+// memory in tiles of 32 rows shared by the 8 queries: for the scores lane j owns key j of the tile
+// (128-d dot product from shared memory, no shuffles); for the weighted sum lane l owns dims
+// [4l, 4l+4).  Row pitch 132 floats keeps the 16-byte shared loads conflict-free.
+constexpr int kCAQ = 8, kCATile = 32, kCAPitch = 132;
+__global__ void __launch_bounds__(kCAQ * 32)
+cross_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n) {
+  extern __shared__ __align__(16) float s_ca[];
+  float* s_q = s_ca;                        // [kCAQ][128]
+  float* s_t = s_q + kCAQ * 128;            // [kCATile][kCAPitch]
+  float* s_p = s_t + kCATile * kCAPitch;    // [kCAQ][n_pad]
+  const int n_tiles = (n + kCATile - 1) / kCATile, n_pad = n_tiles * kCATile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, qi = blockIdx.x * kCAQ + warp;
+  const bool q_ok = qi < n;
+  {
+    const float4 q = q_ok ? *reinterpret_cast<const float4*>(qkv + static_cast<long long>(qi) * 1536 + head * 128 + lane * 4)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(s_q + warp * 128 + lane * 4) = q;
+  }
+  auto load_tile = [&](int t, int col0) {  // rows [32t, 32t+32) of K (col0 = 512) or V (col0 = 1024)
+#pragma unroll
+    for (int i = 0; i < (kCATile * 32) / (kCAQ * 32); ++i) {
+      const int idx = threadIdx.x + i * kCAQ * 32;
+      const int r = idx >> 5, c4 = (idx & 31) * 4;
+      const int j = t * kCATile + r;
+      const float4 v = j < n ? __ldg(reinterpret_cast<const float4*>(qkv + static_cast<long long>(j) * 1536 + col0 +
+                                                                      head * 128 + c4))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(s_t + r * kCAPitch + c4) = v;
+    }
+  };
   const float scale = 0.08838834764831845f;
+  float* p = s_p + warp * n_pad;
   float mx = -FLT_MAX;
-  for (int j = 0; j < n; ++j) {
-    const float4 kv = *reinterpret_cast<const float4*>(qkv + static_cast<long long>(j) * 1536 + 512 + head * 128 + lane * 4);
-    float d = q.x * kv.x + q.y * kv.y + q.z * kv.z + q.w * kv.w;
-    d = warp_sum(d) * scale;
-    if (lane == 0) p[j] = d;
+  for (int t = 0; t < n_tiles; ++t) {
+    __syncthreads();  // previous tile fully consumed (and s_q visible on the first trip)
+    load_tile(t, 512);
+    __syncthreads();
+    const float* kr = s_t + lane * kCAPitch;
+    const float* qr = s_q + warp * 128;
+    float d = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < 128; c += 4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(kr + c);
+      const float4 q4 = *reinterpret_cast<const float4*>(qr + c);
+      d = fmaf(q4.x, k4.x, d);
+      d = fmaf(q4.y, k4.y, d);
+      d = fmaf(q4.z, k4.z, d);
+      d = fmaf(q4.w, k4.w, d);
+    }
+    const int j = t * kCATile + lane;
+    d = j < n ? d * scale : -FLT_MAX;
+    p[j] = d;
     mx = fmaxf(mx, d);
   }
-  __syncwarp();
+  __syncwarp();  // p[] is read lane-strided below
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.f;
-  for (int j = lane; j < n; j += 32) {
-    const float e = __expf(p[j] - mx);
+  for (int j = lane; j < n_pad; j += 32) {
+    const float e = j < n ? __expf(p[j] - mx) : 0.f;
     p[j] = e;
     sum += e;
   }
   sum = warp_sum(sum);
-  __syncwarp();
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = 0; j < n; ++j) {
-    const float pj = p[j];
-    const float4 v = *reinterpret_cast<const float4*>(qkv + static_cast<long long>(j) * 1536 + 1024 + head * 128 + lane * 4);
-    acc.x += pj * v.x; acc.y += pj * v.y; acc.z += pj * v.z; acc.w += pj * v.w;
+  for (int t = 0; t < n_tiles; ++t) {
+    __syncthreads();
+    load_tile(t, 1024);
+    __syncthreads();
+    const float* pt = p + t * kCATile;
+#pragma unroll 8
+    for (int j = 0; j < kCATile; ++j) {
+      const float pj = pt[j];
+      const float4 v = *reinterpret_cast<const float4*>(s_t + j * kCAPitch + lane * 4);
+      acc.x = fmaf(pj, v.x, acc.x);
+      acc.y = fmaf(pj, v.y, acc.y);
+      acc.z = fmaf(pj, v.z, acc.z);
+      acc.w = fmaf(pj, v.w, acc.w);
+    }
   }
-  const float inv = 1.f / sum;
-  *reinterpret_cast<float4*>(out + static_cast<long long>(qi) * 512 + head * 128 + lane * 4) =
-      make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  if (q_ok) {
+    const float inv = 1.f / sum;
+    *reinterpret_cast<float4*>(out + static_cast<long long>(qi) * 512 + head * 128 + lane * 4) =
+        make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
 }
 
 __global__ void argmax_pose_kernel(const float* __restrict__ scores, const float* __restrict__ poses, int n,
@@ -343,15 +437,29 @@ void launch_token_mean(const __half* x, float* out, int n, cudaStream_t s) {
 
 void launch_small_linear(const float* in, const float* w, const float* b, float* out, int rows, int k, int outs,
                          cudaStream_t s) {
-  if (rows <= 0) return;
-  dim3 grid((rows + kSLRows - 1) / kSLRows, (outs + 63) / 64);
-  small_linear_kernel<<<grid, 256, sizeof(float) * kSLRows * k, s>>>(in, w, b, out, rows, k, outs);
+  if (rows <= 0 || outs <= 0) return;
+  if (k % 4 != 0) throw std::invalid_argument("small_linear: k must be a multiple of 4");
+  if (outs == 1) {
+    row_dot_kernel<<<(rows * 32 + 127) / 128, 128, 0, s>>>(in, w, b, out, rows, k);
+    return;
+  }
+  dim3 grid((rows + kSGTile - 1) / kSGTile, (outs + kSGTile - 1) / kSGTile);
+  small_linear_kernel<<<grid, 256, 0, s>>>(in, w, b, out, rows, k, outs);
 }
 
 void launch_cross_attention(const float* qkv, float* out, int n, cudaStream_t s) {
   if (n <= 0) return;
-  const int warps = 4;
-  cross_attention_kernel<<<(n * 4 + warps - 1) / warps, warps * 32, sizeof(float) * warps * n, s>>>(qkv, out, n);
+  const int n_pad = (n + kCATile - 1) / kCATile * kCATile;
+  const size_t smem = sizeof(float) * (kCAQ * 128 + kCATile * kCAPitch + (size_t)kCAQ * n_pad);
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    if (smem > 200 * 1024) throw std::invalid_argument("cross_attention: too many hypotheses for one shared-memory score row");
+    if (cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      throw std::runtime_error("cudaFuncSetAttribute(cross_attention smem) failed");
+    smem_set = smem;
+  }
+  dim3 grid((n + kCAQ - 1) / kCAQ, 4);
+  cross_attention_kernel<<<grid, kCAQ * 32, smem, s>>>(qkv, out, n);
 }
 
 void launch_argmax_pose(const float* scores, const float* poses, int n, int* best_index, float* best_pose,

@@ -10,6 +10,7 @@ namespace fpb {
 const char* attention_init();
 // qkv: [n_hyp*400, qkv_ld] fp16 with Q | K | V blocks of 4 heads x 128; out: [n_hyp*400, out_ld].
 void launch_attention(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, cudaStream_t s);
+bool attention_phase_clocks(unsigned long long out[22]);
 
 // out = LayerNorm(x) * gamma + beta over 512 channels, eps 1e-5 (post-LN of nn.TransformerEncoderLayer;
 // the residual sum x = a + sublayer(a) is formed by the producing GEMM's epilogue).  [rows,512] fp16.

@@ -349,13 +349,13 @@ void do_score_features(fpb200_session* s) {
   // out_proj of the self-attention applied to the token mean (linear, so it commutes with the mean)
   launch_small_linear(s->arena->mean_t, W.f32("att.out.w", 512, 512), W.f32("att.out.b", 512), s->feats.p, nl, 512,
                       512, s->stream);
-  pack_exchange_kernel<<<(nl * kExchLd + 255) / 256, 256, 0, s->stream>>>(s->feats.p, s->poses.p + 16 * s->lo,
-                                                                         s->exch_local.p, nl);
-  FPB_CUDA(cudaGetLastError());
-  if (s->opt.shard_world == 1)
-    FPB_CUDA(cudaMemcpyAsync(s->exch_all.p, s->exch_local.p, sizeof(float) * (size_t)nl * kExchLd,
-                             cudaMemcpyDeviceToDevice, s->stream));
-  s->count_launches(s->scorer->launches_per_forward(nl) + 2);
+  // The exchange rows only exist to cross GPUs; a single-GPU session ranks straight from feats / poses.
+  if (s->opt.shard_world > 1) {
+    pack_exchange_kernel<<<(nl * kExchLd + 255) / 256, 256, 0, s->stream>>>(s->feats.p, s->poses.p + 16 * s->lo,
+                                                                           s->exch_local.p, nl);
+    FPB_CUDA(cudaGetLastError());
+  }
+  s->count_launches(s->scorer->launches_per_forward(nl) + (s->opt.shard_world > 1 ? 2 : 1));
   s->features_ready = true;
 }
 
@@ -363,17 +363,21 @@ void do_score_finish(fpb200_session* s) {
   FPB_REQUIRE(s->features_ready, "score_features must run before score_finish");
   const int n = s->n_hyp;
   const WeightFile& W = s->scorer->weights();
-  unpack_exchange_kernel<<<(n * kExchLd + 255) / 256, 256, 0, s->stream>>>(s->exch_all.p, s->feats.p, s->all_poses.p, n,
-                                                                          s->opt.shard_world, s->shard_cap);
-  FPB_CUDA(cudaGetLastError());
+  const float* all_poses = s->poses.p;
+  if (s->opt.shard_world > 1) {
+    unpack_exchange_kernel<<<(n * kExchLd + 255) / 256, 256, 0, s->stream>>>(s->exch_all.p, s->feats.p, s->all_poses.p,
+                                                                            n, s->opt.shard_world, s->shard_cap);
+    FPB_CUDA(cudaGetLastError());
+    all_poses = s->all_poses.p;
+  }
   launch_small_linear(s->feats.p, W.f32("cross.qkv.w", 1536, 512), W.f32("cross.qkv.b", 1536), s->tail_qkv.p, n, 512,
                       1536, s->stream);
   launch_cross_attention(s->tail_qkv.p, s->tail_att.p, n, s->stream);
   launch_small_linear(s->tail_att.p, W.f32("cross.out.w", 512, 512), W.f32("cross.out.b", 512), s->tail_out.p, n, 512,
                       512, s->stream);
   launch_small_linear(s->tail_out.p, W.f32("lin.w", 1, 512), W.f32("lin.b", 1), s->scores.p, n, 512, 1, s->stream);
-  launch_argmax_pose(s->scores.p, s->all_poses.p, n, s->best_index.p, s->best_pose.p, s->stream);
-  s->count_launches(6);
+  launch_argmax_pose(s->scores.p, all_poses, n, s->best_index.p, s->best_pose.p, s->stream);
+  s->count_launches(s->opt.shard_world > 1 ? 6 : 5);
 }
 
 // Single device->host read of the call: winning pose, its index and the status word.

@@ -192,6 +192,18 @@ int fpb200_debug_conv_gemm(const fpb200_conv_desc* desc, int repeat, float* ms_o
  * reference, trt_core.cpp:367): qkv [n_hyp*400, 1536] fp16 (Q | K | V, 4 heads x 128) ->
  * out [n_hyp*400, 512] fp16.  Runs once + `repeat` timed launches on the default stream. */
 int fpb200_debug_attention(const void* qkv, void* out, int n_hyp, int repeat, float* ms_out);
+/* With FPB200_ATTN_PHASES=1 in the environment: SM-clock sums of the last attention launch spent by one
+ * softmax thread of CTA 0 in {wait S, row max, exp + P store, wait O, epilogue TMEM -> staging,
+ * store issue}, then its item count; 7 values for the full 128-row tiles, 7 for the 16-row tail tiles,
+ * 2 unused, then 6 sums of the MMA-issuing thread {wait Q, wait K, wait O drained, wait V, wait P steps, issue}. */
+int fpb200_debug_attention_phases(unsigned long long out[22]);
+
+/* fp32 operators of the scorer tail (after the token mean; inside the scorer engine in the reference):
+ * out[rows, outs] = in[rows, k] w[outs, k]^T + b (b may be NULL), and the cross-hypothesis attention
+ * qkv [n, 1536] (Q | K | V, 4 heads x 128) -> out [n, 512].  Once + `repeat` timed launches. */
+int fpb200_debug_small_linear(const float* in, const float* w, const float* b, float* out, int rows, int k, int outs,
+                              int repeat, float* ms_out);
+int fpb200_debug_cross_attention(const float* qkv, float* out, int n, int repeat, float* ms_out);
 
 const char* fpb200_last_error(void);
 

@@ -10,3 +10,15 @@ out = torch.empty(n, 400, 512, device="cuda", dtype=torch.float16)
 ms = capi.debug_attention(qkv.data_ptr(), out.data_ptr(), n, 20)
 fl = 2.0 * n * 4 * 2 * 400 * 400 * 128
 print(f"attention n={n}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s (algorithmic)")
+if os.environ.get("FPB200_ATTN_PHASES"):
+    import ctypes as C
+    buf = (C.c_ulonglong * 22)()
+    capi.check(capi.lib().fpb200_debug_attention_phases(buf))
+    names = ["wait S", "pass 1 (max)", "pass 2 (exp)", "wait O", "epi tmem->smem", "store issue"]
+    for kind, o in (("full tiles", 0), ("tail tiles", 7)):
+        items = max(1, buf[o + 6])
+        print(f"CTA 0, {kind} (SM clocks per item): " + ", ".join(f"{nm} {buf[o + i] / items:.0f}" for i, nm in enumerate(names))
+              + f"; items {buf[o + 6]}, total/item {sum(buf[o:o + 6]) / items:.0f}")
+    n_it = max(1, buf[6] + buf[13])
+    mn = ["wait Q", "wait K", "wait O drained", "wait V", "wait P steps", "issue/other"]
+    print("CTA 0, MMA thread (SM clocks per item): " + ", ".join(f"{nm} {buf[16 + i] / n_it:.0f}" for i, nm in enumerate(mn)))
