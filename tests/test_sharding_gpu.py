@@ -1,0 +1,85 @@
+"""Hypothesis sharding at BASELINE size (N = 252) on ONE GPU: `world` sessions with shard_rank = 0..world-1
+run their contiguous hypothesis ranges, their exchange rows ([n_local, 528] f32 = 512-d scorer feature +
+refined pose) are concatenated by hand where the multi-GPU run calls ncclAllGather (bench.py: gather()), and
+every rank's score_finish must return the unsharded session's winner.  Per-hypothesis work does not depend
+on which other hypotheses share a launch (fixed K-loop order per output element), so equality is exact.
+The reference has no multi-GPU path; the scorer's cross-hypothesis attention
+ is why features, not scores, are exchanged."""
+import numpy as np
+import pytest
+import torch
+
+from foundationpose_cpp_b200 import api, sharding, synth
+import fp_helpers as helpers
+
+pytestmark = pytest.mark.gpu
+N = 252
+
+
+class _DevMem:
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _dev(ptr, n):
+    return torch.as_tensor(_DevMem(ptr, n), device="cuda:0")
+
+
+@pytest.fixture(scope="module")
+def setup(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("weights"))
+    rp, sp = helpers.write_seeded_weights(d)
+    mesh = synth.uv_ellipsoid("obj", slices=64, stacks=33, tex_size=256, seed=0)
+    rgb, depth, mask, _ = synth.make_scene(mesh)
+
+    def make(rank, world):
+        return api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], synth.DEFAULT_K,
+                                             max_h=480, max_w=640, max_hyps=N, shard_rank=rank, shard_world=world)
+
+    ref = make(0, 1)
+    ok, pose = ref.Register(rgb, depth, mask, "obj", refine_itr=1)
+    assert ok, ref.last_error
+    scores = ref.read_buffer("scores", np.float32, N).copy()
+    ref.close()
+    return {"make": make, "rgb": rgb, "depth": depth, "mask": mask, "pose": pose, "scores": scores}
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_register_equals_single_session(setup, world):
+    cap = sharding.shard_capacity(N, world)
+    gathered = torch.zeros(world * cap * sharding.EXCH_LD, device="cuda:0")
+    sizes = []
+    # pass 1: every rank produces its exchange rows (one session alive at a time: the arena is per session)
+    for r in range(world):
+        m = setup["make"](r, world)
+        m.upload(setup["rgb"], setup["depth"])
+        m.sample_hypotheses(setup["mask"], "obj")
+        m.refine_step()
+        m.score_features()
+        lp, nl, off, ap, na = m.feature_buffers()
+        lo, hi = sharding.shard_range(N, r, world)
+        assert (nl, off, na) == (hi - lo, lo, N)
+        sizes.append(nl)
+        torch.cuda.synchronize()
+        seg = cap * sharding.EXCH_LD
+        gathered[r * seg:(r + 1) * seg].copy_(_dev(lp, seg))  # what ncclAllGather does with rank r's buffer
+        torch.cuda.synchronize()
+        m.close()
+    assert sum(sizes) == N and max(sizes) - min(sizes) <= 1
+    # pass 2: any rank finishes from the gathered rows (first and last: the uneven split differs between them)
+    for r in (0, world - 1):
+        m = setup["make"](r, world)
+        m.upload(setup["rgb"], setup["depth"])
+        m.sample_hypotheses(setup["mask"], "obj")
+        m.refine_step()
+        m.score_features()
+        lp, nl, off, ap, na = m.feature_buffers()
+        torch.cuda.synchronize()
+        _dev(ap, world * cap * sharding.EXCH_LD).copy_(gathered)
+        torch.cuda.synchronize()
+        idx, pose = m.score_finish()
+        scores = m.read_buffer("scores", np.float32, N)
+        m.close()
+        assert idx == int(np.argmax(setup["scores"]))
+        assert np.array_equal(scores, setup["scores"]), float(np.abs(scores - setup["scores"]).max())
+        assert np.array_equal(pose, setup["pose"])
