@@ -506,11 +506,25 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   if ((d.bw & (d.bw - 1)) || (d.bh & (d.bh - 1))) return "conv_gemm: bw and bh must be powers of two";
   if (d.cin % kGemmBlockK != 0) return "conv_gemm: cin must be a multiple of 64";
   if (d.num_taps < 1 || d.num_taps > kMaxTaps) return "conv_gemm: bad tap count";
-  int bn_tile = 0;
-  if (d.cout % 256 == 0) bn_tile = 256;
-  else if (d.cout % 128 == 0) bn_tile = 128;
-  else if (d.cout % 64 == 0) bn_tile = 64;
-  else return "conv_gemm: cout must be a multiple of 64";
+  if (d.cout % 64 != 0) return "conv_gemm: cout must be a multiple of 64";
+  // Tile width: the widest of 256 / 128 / 64 that divides cout (fewest activation re-reads), unless the
+  // launch then has fewer tiles than SMs (Track: N = 1 hypothesis, 4..100 row tiles per layer): a small
+  // launch is bound by the serial K loop of its few CTAs, so narrower tiles (4x more CTAs, 4x shorter
+  // MMAs) cut its latency.  Accumulation order per output element is the same for every width.
+  int bn_tile = 64;
+  {
+    const long long m_tiles = (long long)((d.out_w + d.bw - 1) / d.bw) * ((d.out_h + d.bh - 1) / d.bh) *
+                              ((d.n_img + d.bn - 1) / d.bn);
+    for (int cand : {256, 128})
+      if (d.cout % cand == 0 && m_tiles * (d.cout / cand) >= g_num_sms) {
+        bn_tile = cand;
+        break;
+      }
+  }
+  if (const char* env = getenv("FPB_GEMM_BN")) {
+    const int v = atoi(env);
+    if ((v == 64 || v == 128 || v == 256) && d.cout % v == 0) bn_tile = v;
+  }
   const int out_ld = d.out_ld ? d.out_ld : d.cout;
   if (out_ld % 8 || d.half_coff % 8) return "conv_gemm: output leading dims must be multiples of 8";
   if (d.out_phase_split && ((d.out_h | d.out_w) & 1)) return "conv_gemm: phase-split needs even H, W";

@@ -95,17 +95,21 @@ layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
 // combined through shared memory in a fixed order (deterministic).
 __global__ void __launch_bounds__(512)
 layernorm_mean_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, float* __restrict__ out) {
+                      const float* __restrict__ beta, float* __restrict__ out, float* __restrict__ partial) {
   __shared__ float part[16][kDim];
   const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // gridDim.y > 1 (few hypotheses, Track): this CTA takes a slice of the tokens and leaves an unscaled
+  // partial sum for layernorm_mean_combine_kernel
+  const int per = (kTok + gridDim.y - 1) / gridDim.y;
+  const int t_begin = blockIdx.y * per, t_end = min(kTok, t_begin + per);
   float g[16], b[16], acc[16];
   load_affine16(gamma, beta, lane, g, b);
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   const long long row0 = static_cast<long long>(n) * kTok;
-  for (int t = warp; t < kTok; t += 32) {
+  for (int t = t_begin + warp; t < t_end; t += 32) {
     float v0[16], v1[16];
-    const bool two = t + 16 < kTok;
+    const bool two = t + 16 < t_end;
     load_row16(x, row0 + t, lane, v0);
     if (two) load_row16(x, row0 + t + 16, lane, v1);
     normalise_row16(v0, g, b);
@@ -126,8 +130,15 @@ layernorm_mean_kernel(const __half* __restrict__ x, const float* __restrict__ ga
     float s = 0.f;
 #pragma unroll 8
     for (int w = 0; w < 16; ++w) s += part[w][threadIdx.x];
-    out[static_cast<long long>(n) * kDim + threadIdx.x] = s * (1.f / kTok);
+    if (gridDim.y == 1) out[static_cast<long long>(n) * kDim + threadIdx.x] = s * (1.f / kTok);
+    else partial[(static_cast<long long>(n) * gridDim.y + blockIdx.y) * kDim + threadIdx.x] = s;
   }
+}
+__global__ void __launch_bounds__(512)
+layernorm_mean_combine_kernel(const float* __restrict__ partial, float* __restrict__ out, int slices) {
+  float s = 0.f;
+  for (int k = 0; k < slices; ++k) s += partial[(static_cast<long long>(blockIdx.x) * slices + k) * kDim + threadIdx.x];
+  out[static_cast<long long>(blockIdx.x) * kDim + threadIdx.x] = s * (1.f / kTok);
 }
 
 // One 1024-thread CTA per hypothesis: four groups of 256 threads each sum 100 tokens (one coalesced
@@ -425,9 +436,14 @@ void launch_layernorm(const __half* x, const float* gamma, const float* beta, __
 }
 
 void launch_layernorm_mean(const __half* x, const float* gamma, const float* beta, float* out, int n,
-                           cudaStream_t s) {
+                           float* partial, cudaStream_t s) {
   if (n <= 0) return;
-  layernorm_mean_kernel<<<n, 512, 0, s>>>(x, gamma, beta, out);
+  if (partial && n <= kLnMeanSliceHyps) {
+    layernorm_mean_kernel<<<dim3(n, kLnMeanSlices), 512, 0, s>>>(x, gamma, beta, out, partial);
+    layernorm_mean_combine_kernel<<<n, 512, 0, s>>>(partial, out, kLnMeanSlices);
+    return;
+  }
+  layernorm_mean_kernel<<<n, 512, 0, s>>>(x, gamma, beta, out, nullptr);
 }
 
 void launch_token_mean(const __half* x, float* out, int n, cudaStream_t s) {

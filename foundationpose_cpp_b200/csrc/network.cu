@@ -85,6 +85,7 @@ Arena::Arena(int max_hyps) : cap(max_hyps) {
       {(void**)&qkv, 3 * tok}, {(void**)&att, tok}, {(void**)&proj, tok}, {(void**)&x1, tok},
       {(void**)&ff1, tok}, {(void**)&ff2, tok}, {(void**)&x2, tok},
       {(void**)&mean_t, n * 512 * 4}, {(void**)&mean_r, n * 512 * 4},
+      {(void**)&mean_part, (size_t)kLnMeanSliceHyps * kLnMeanSlices * 512 * 4},
   };
   size_t total = 0;
   for (auto& it : items) total += (it.bytes + 1023) / 1024 * 1024;
@@ -216,7 +217,7 @@ void Network::add_encoder_layer(Plan& p, int n, const std::string& h, float* mea
   add_gemm(p.steps, &p.flops, linear_desc(A.ff1, rows, 512, W.f16(h + ".ff2.w", 512, 512), W.f32(h + ".ff2.b", 512), 512, A.ff2, false, A.x1));
   const float *g2 = W.f32(h + ".ln2.g", 512), *b2 = W.f32(h + ".ln2.b", 512);
   // the second LayerNorm's tokens are consumed only through their mean: fused, never stored
-  p.steps.push_back([&A, n, g2, b2, mean_out](cudaStream_t s) { launch_layernorm_mean(A.ff2, g2, b2, mean_out, n, s); });
+  p.steps.push_back([&A, n, g2, b2, mean_out](cudaStream_t s) { launch_layernorm_mean(A.ff2, g2, b2, mean_out, n, A.mean_part, s); });
   p.flops += 2.0 * n * 512 * 3;  // Linear(512,3) on the token mean
 }
 
@@ -290,6 +291,9 @@ void Network::collect_profile(double* ms, double* flops, long long* launches) {
   ev_flops_.clear();
 }
 
-int Network::launches_per_forward(int n) { return (int)plan(n).steps.size(); }
+int Network::launches_per_forward(int n) {
+  // the sliced LayerNorm + mean of the two refiner heads is two kernels per step for few hypotheses
+  return (int)plan(n).steps.size() + (kind_ == NetKind::kRefiner && n <= kLnMeanSliceHyps ? 2 : 0);
+}
 
 }  // namespace fpb

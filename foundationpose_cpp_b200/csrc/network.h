@@ -46,6 +46,7 @@ struct Arena {
          *c1 = nullptr, *c2 = nullptr, *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *qkv = nullptr,
          *att = nullptr, *proj = nullptr, *x1 = nullptr, *ff1 = nullptr, *ff2 = nullptr, *x2 = nullptr;
   float *mean_t = nullptr, *mean_r = nullptr;
+  float* mean_part = nullptr;  // partial sums of the sliced LayerNorm + token mean (few hypotheses)
   void* blob = nullptr;
   size_t bytes = 0;
   explicit Arena(int max_hyps);

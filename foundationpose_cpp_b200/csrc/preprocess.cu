@@ -4,6 +4,7 @@
 #include "preprocess.h"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace fpb {
 
@@ -386,34 +387,24 @@ __device__ __forceinline__ void setup_pleq(float z0, float z1, float z2, int v0x
   pl[2] = z;
 }
 
-// One CTA per (band of 40 rows, hypothesis).  Phase 1: every thread takes triangles, does
-// cudaraster's triangle setup (TriangleSetup.inl fast path) and resolves visibility with a 64-bit
-// atomicMin on a shared-memory z-buffer whose key is (u32 depth << 32) | ~triangle, i.e. nearest wins
-// and on equal depth the later triangle wins (FineRaster.inl:152-172,338-351).  Phase 2: per pixel,
-// nvdiffrast's barycentrics / interpolation / texture (rasterize.cu:55-89, interpolate.cu:46-76,
-// texture.cu:19-96), the reference's shading (foundationpose_render.cu:459-501), vertical flip
-// (foundationpose_render.cpp:676-680), normalisation and packing (foundationpose_render.cu:61-140).
-__global__ void __launch_bounds__(kRenderThreads, 4)
-render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vclip,
-              const float4* __restrict__ vattr, __half* __restrict__ packed, int img0,
-              int32_t* __restrict__ rast_id_debug, int* __restrict__ status) {
-  extern __shared__ unsigned long long zbuf[];  // [kTileRows * 160]
-  const int pose = blockIdx.y;
-  const int row0 = blockIdx.x * kTileRows;  // GL rows [row0, row0 + kTileRows)
-  for (int i = threadIdx.x; i < kCrop * kTileRows; i += blockDim.x) zbuf[i] = ~0ull;
-  __syncthreads();
-
+// Visibility of the triangles t = t_first + i * t_stride (i = 0, 1, ...) inside GL rows [row0, row0 + nrows)
+// of one hypothesis: cudaraster's triangle setup (TriangleSetup.inl fast path) and a 64-bit atomicMin per
+// covered sample on a z-buffer (shared or global memory, row pitch 160) whose key is (u32 depth << 32) |
+// ~triangle, i.e. nearest wins and on equal depth the later triangle wins (FineRaster.inl:152-172,338-351);
+// the result does not depend on the order in which triangles arrive.  Returns whether some triangle would
+// have taken cudaraster's clip path.
+__device__ __forceinline__ bool raster_triangles(const DeviceMesh& mesh, const float4* __restrict__ pc, int t_first,
+                                                 int t_stride, int row0, int nrows, unsigned long long* zbuf) {
   constexpr int W = kCrop, H = kCrop;
   const float vs = (float)(W << 3);
   constexpr int bias = (W - 1) << 3;  // sample x of pixel px = px*16 - bias
-  const float4* pc = vclip + (long long)pose * mesh.num_vertices;
   bool clip_path = false;
   // Warp-uniform trip count and a single `live` flag instead of `continue`s: the lanes of a warp
   // reconverge at every iteration (with early exits the compiler let them drift apart and the loop
   // ran with ~6 active lanes).
-  const int n_iter = (mesh.num_faces + blockDim.x - 1) / blockDim.x;
+  const int n_iter = (mesh.num_faces + t_stride - 1) / t_stride;
   for (int it = 0; it < n_iter; ++it) {
-    const int t = it * blockDim.x + threadIdx.x;
+    const int t = it * t_stride + t_first;
     bool live = t < mesh.num_faces;
     int i0 = 0, i1 = 0, i2 = 0;
     if (live) {
@@ -451,7 +442,7 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4
       live = false;
     }
     const int px0 = max((lox + bias + 15) >> 4, 0), px1 = min((hix + bias) >> 4, W - 1);
-    const int py0 = max((loy + bias + 15) >> 4, row0), py1 = min((hiy + bias) >> 4, row0 + kTileRows - 1);
+    const int py0 = max((loy + bias + 15) >> 4, row0), py1 = min((hiy + bias) >> 4, row0 + nrows - 1);
     if (px0 > px1 || py0 > py1) live = false;  // no sample of this band inside the bounding box
     int d1x = p1x - p0x, d1y = p1y - p0y, d2x = p2x - p0x, d2y = p2y - p0y;
     int area = d1x * d2y - d1y * d2x;
@@ -498,17 +489,25 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4
     }
     __syncwarp();
   }
-  if (clip_path) atomicOr(status, kStatusClipPath);
-  __syncthreads();
+  return clip_path;
+}
 
-  // ---- phase 2: shade
+// Per pixel of GL rows [row0, row0 + nrows) (z-buffer row pitch 160, first row = row0): nvdiffrast's
+// barycentrics / interpolation / texture (rasterize.cu:55-89, interpolate.cu:46-76, texture.cu:19-96), the
+// reference's shading (foundationpose_render.cu:459-501), vertical flip (foundationpose_render.cpp:676-680),
+// normalisation and packing (foundationpose_render.cu:61-140).
+__device__ __forceinline__ void shade_pixels(const DeviceMesh& mesh, const PoseAux* __restrict__ aux_all,
+                                             const float4* __restrict__ pc, const float4* __restrict__ vattr,
+                                             __half* __restrict__ packed, int img0, int32_t* __restrict__ rast_id_debug,
+                                             int pose, int row0, int nrows, const unsigned long long* zbuf) {
+  constexpr int W = kCrop, H = kCrop;
   const float xs = 2.0f / (float)W, xo = 1.0f / (float)W - 1.0f;
   const float ys = 2.0f / (float)H, yo = 1.0f / (float)H - 1.0f;
   const float half_d = mesh.diameter / 2.f;
   const float4* pa = vattr + (long long)pose * mesh.num_vertices;
   const float t_x = aux_all[pose].t[0], t_y = aux_all[pose].t[1], t_z = aux_all[pose].t[2];
   __half* img = packed + (long long)(img0 + pose) * kPackImageElems;
-  for (int i = threadIdx.x; i < W * kTileRows; i += blockDim.x) {
+  for (int i = threadIdx.x; i < W * nrows; i += blockDim.x) {
     const int ly = i / W, px = i - ly * W;
     const int py = row0 + ly;
     const unsigned long long key = zbuf[i];
@@ -581,6 +580,46 @@ render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4
     hp[3] = __floats2half2_rn(0.f, 0.f);
     *reinterpret_cast<uint4*>(img + ((long long)yimg * kStemPitch + kStemPad + px) * kPackC) = pk;
   }
+}
+
+// One CTA per (band of 40 rows, hypothesis): every thread takes triangles and resolves visibility on a
+// shared-memory z-buffer (raster_triangles), then the band is shaded (shade_pixels).
+__global__ void __launch_bounds__(kRenderThreads, 4)
+render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vclip,
+              const float4* __restrict__ vattr, __half* __restrict__ packed, int img0,
+              int32_t* __restrict__ rast_id_debug, int* __restrict__ status) {
+  extern __shared__ unsigned long long zbuf[];  // [kTileRows * 160]
+  const int pose = blockIdx.y;
+  const int row0 = blockIdx.x * kTileRows;  // GL rows [row0, row0 + kTileRows)
+  for (int i = threadIdx.x; i < kCrop * kTileRows; i += blockDim.x) zbuf[i] = ~0ull;
+  __syncthreads();
+  const float4* pc = vclip + (long long)pose * mesh.num_vertices;
+  if (raster_triangles(mesh, pc, threadIdx.x, blockDim.x, row0, kTileRows, zbuf)) atomicOr(status, kStatusClipPath);
+  __syncthreads();
+  shade_pixels(mesh, aux_all, pc, vattr, packed, img0, rast_id_debug, pose, row0, kTileRows, zbuf);
+}
+
+// Few hypotheses (Track: one): a (band, hypothesis) grid would leave most SMs idle while 4 CTAs walk all
+// triangles, so the triangles are spread over blockIdx.x CTAs as well, on a global z-buffer of the whole
+// crop (pre-set to ~0), and the crop is shaded by a second kernel.  Same keys, same atomicMin: the
+// visibility result is identical to render_kernel's.
+__global__ void __launch_bounds__(kRenderThreads)
+raster_split_kernel(DeviceMesh mesh, const float4* __restrict__ vclip, unsigned long long* __restrict__ zbuf_all,
+                    int* __restrict__ status) {
+  const int pose = blockIdx.y;
+  const float4* pc = vclip + (long long)pose * mesh.num_vertices;
+  if (raster_triangles(mesh, pc, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, 0, kCrop,
+                       zbuf_all + (long long)pose * kCrop * kCrop))
+    atomicOr(status, kStatusClipPath);
+}
+__global__ void __launch_bounds__(kRenderThreads)
+shade_split_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vclip,
+                   const float4* __restrict__ vattr, __half* __restrict__ packed, int img0,
+                   int32_t* __restrict__ rast_id_debug, const unsigned long long* __restrict__ zbuf_all, int rows) {
+  const int pose = blockIdx.y;
+  const int row0 = blockIdx.x * rows;
+  shade_pixels(mesh, aux_all, vclip + (long long)pose * mesh.num_vertices, vattr, packed, img0, rast_id_debug, pose,
+               row0, rows, zbuf_all + (long long)pose * kCrop * kCrop + (long long)row0 * kCrop);
 }
 
 // ------------------------------------------------------------------ observed crop
@@ -705,12 +744,33 @@ void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float dia
   pose_setup_kernel<<<(n + 63) / 64, 64, 0, s>>>(poses, n, K, diameter, crop_ratio, aux);
 }
 
-void launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr, __half* packed,
-                   int img0, int32_t* rast_id_debug, int* status, cudaStream_t s) {
-  if (n <= 0) return;
+int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr, __half* packed,
+                  int img0, int32_t* rast_id_debug, int* status, unsigned long long* zbuf_scratch, int zbuf_poses,
+                  cudaStream_t s) {
+  if (n <= 0) return 0;
   vertex_stage_kernel<<<dim3((mesh.num_vertices + 255) / 256, n), 256, 0, s>>>(mesh, aux, vclip, vattr);
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  bool split = n * kRenderTiles * 4 <= sms;
+  if (const char* e = getenv("FPB200_RENDER_SPLIT")) split = e[0] != '0';  // tests run both paths on the same input
+  if (split && zbuf_scratch && n <= zbuf_poses) {
+    // few hypotheses: spread the triangles over the machine (see raster_split_kernel)
+    cudaMemsetAsync(zbuf_scratch, 0xFF, sizeof(unsigned long long) * (size_t)n * kCrop * kCrop, s);
+    const int want = sms / n, have = (mesh.num_faces + kRenderThreads - 1) / kRenderThreads;
+    const int slices = want < have ? (want < 1 ? 1 : want) : have;
+    raster_split_kernel<<<dim3(slices, n), kRenderThreads, 0, s>>>(mesh, vclip, zbuf_scratch, status);
+    constexpr int kShadeRows = 8;
+    shade_split_kernel<<<dim3(kCrop / kShadeRows, n), kRenderThreads, 0, s>>>(mesh, aux, vclip, vattr, packed, img0,
+                                                                             rast_id_debug, zbuf_scratch, kShadeRows);
+    return 3;
+  }
   render_kernel<<<dim3(kRenderTiles, n), kRenderThreads, kCrop * kTileRows * 8, s>>>(mesh, aux, vclip, vattr, packed,
                                                                                       img0, rast_id_debug, status);
+  return 2;
 }
 
 void launch_warp(const uint8_t* rgb, const float* xyz, int h, int w, const PoseAux* aux, int n, float diameter,

@@ -63,9 +63,14 @@ void launch_fill_hypotheses(const float* grid, const float* center, float* poses
 void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float diameter,
                        float crop_ratio, PoseAux* aux, cudaStream_t s);
 // Vertex stage + rasterise + shade + flip + normalise + pack hypothesis i into packed image
-// `img0 + i`.  vclip / vattr: scratch of n * num_vertices float4 each.
-void launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr,
-                   __half* packed, int img0, int32_t* rast_id_debug, int* status, cudaStream_t s);
+// `img0 + i`.  vclip / vattr: scratch of n * num_vertices float4 each.  zbuf_scratch (may be null):
+// zbuf_poses * 160 * 160 keys; with n <= zbuf_poses and few enough hypotheses to leave SMs idle the
+// triangles are spread over the whole machine on global z-buffers (identical result).
+constexpr int kSplitRenderPoses = 8;
+// Returns the number of kernels launched.
+int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr,
+                   __half* packed, int img0, int32_t* rast_id_debug, int* status,
+                   unsigned long long* zbuf_scratch, int zbuf_poses, cudaStream_t s);
 // Crop/warp the observed rgb + xyz, normalise, pack into packed image `img0 + i`.
 void launch_warp(const uint8_t* rgb, const float* xyz, int h, int w, const PoseAux* aux, int n,
                  float diameter, __half* packed, int img0, cudaStream_t s);

@@ -174,6 +174,7 @@ struct fpb200_session {
   DevBuf<int> status, best_index;
   DevBuf<unsigned> sampler_scratch;
   DevBuf<int32_t> rast_id;
+  DevBuf<unsigned long long> zbuf;  // whole-crop z-buffers of the few-hypotheses render path
   DevBuf<PoseAux> aux;
   DevBuf<float4> vclip, vattr;  // vertex-stage output [local hypotheses][max vertices]
   HostResult* host_result = nullptr;  // pinned
@@ -296,9 +297,10 @@ void do_render_and_transform(fpb200_session* s, float crop_ratio) {
   const int nl = s->hi - s->lo;
   const MeshEntry& m = *s->cur_mesh;
   launch_pose_setup(s->poses.p + 16 * s->lo, nl, s->intr, m.dm.diameter, crop_ratio, s->aux.p, s->stream);
-  launch_render(m.dm, s->aux.p, nl, s->vclip.p, s->vattr.p, s->arena->packed, 0, s->rast_id.p, s->status.p, s->stream);
+  const int k_render = launch_render(m.dm, s->aux.p, nl, s->vclip.p, s->vattr.p, s->arena->packed, 0, s->rast_id.p,
+                                     s->status.p, s->zbuf.p, kSplitRenderPoses, s->stream);
   launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->stream);
-  s->count_launches(4);
+  s->count_launches(2 + k_render);
   s->crop_ratio_last = crop_ratio;
 }
 
@@ -547,6 +549,7 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
     s->poses.alloc((size_t)cap * 16); s->all_poses.alloc((size_t)cap * 16);
     s->center.alloc(4); s->status.alloc(1); s->best_index.alloc(1); s->best_pose.alloc(16);
     s->aux.alloc(cap); s->rast_id.alloc((size_t)cap * kCrop * kCrop);
+    s->zbuf.alloc((size_t)std::min(cap, kSplitRenderPoses) * kCrop * kCrop);
     s->exch_local.alloc((size_t)cap * kExchLd);
     s->exch_all.alloc(((size_t)cap + s->opt.shard_world) * kExchLd);
     s->feats.alloc((size_t)cap * 512); s->tail_qkv.alloc((size_t)cap * 1536); s->tail_att.alloc((size_t)cap * 512);

@@ -81,8 +81,12 @@ def _fp16_close(got, ref, what):
     assert frac <= 1e-3, f"{what}: {frac:.2e} of elements differ from the fp16-rounded oracle"
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
 @pytest.mark.parametrize("crop_ratio", [1.2, 1.1])
-def test_render_and_transform_parity(env, crop_ratio):
+def test_render_and_transform_parity(env, crop_ratio, split, monkeypatch):
+    # split = "1": the few-hypotheses path (triangles spread over all SMs on global z-buffers, then a shading
+    # kernel: what Track uses); "0": one CTA per (band, hypothesis) on a shared-memory z-buffer (Register)
+    monkeypatch.setenv("FPB200_RENDER_SPLIT", split)
     m = env["model"]
     m.upload(env["rgb"], env["depth"])
     poses = O.sample_hypotheses(env["depth"], env["mask"], env["K"])[[0, 7, 50, 101, 200, 251]]
