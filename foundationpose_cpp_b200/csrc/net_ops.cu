@@ -438,12 +438,10 @@ void launch_layernorm(const __half* x, const float* gamma, const float* beta, __
 void launch_layernorm_mean(const __half* x, const float* gamma, const float* beta, float* out, int n,
                            float* partial, cudaStream_t s) {
   if (n <= 0) return;
-  if (partial && n <= kLnMeanSliceHyps) {
-    layernorm_mean_kernel<<<dim3(n, kLnMeanSlices), 512, 0, s>>>(x, gamma, beta, out, partial);
-    layernorm_mean_combine_kernel<<<n, 512, 0, s>>>(partial, out, kLnMeanSlices);
-    return;
-  }
-  layernorm_mean_kernel<<<n, 512, 0, s>>>(x, gamma, beta, out, nullptr);
+  // always kLnMeanSlices token slices per hypothesis, whatever n: the summation order (and so the result)
+  // does not depend on how many hypotheses share the launch (sharded == unsharded, Track == Register)
+  layernorm_mean_kernel<<<dim3(n, kLnMeanSlices), 512, 0, s>>>(x, gamma, beta, out, partial);
+  layernorm_mean_combine_kernel<<<n, 512, 0, s>>>(partial, out, kLnMeanSlices);
 }
 
 void launch_token_mean(const __half* x, float* out, int n, cudaStream_t s) {

@@ -17,9 +17,10 @@ bool attention_phase_clocks(unsigned long long out[22]);
 void launch_layernorm(const __half* x, const float* gamma, const float* beta, __half* out, long long rows,
                       cudaStream_t s);
 // out[n,512] f32 = mean over the 400 tokens of LayerNorm(x[n,400,512]); the normalised tokens are not stored.
-// partial (may be null): kLnMeanSliceHyps * kLnMeanSlices * 512 floats; with n <= kLnMeanSliceHyps the tokens
-// of a hypothesis are split over kLnMeanSlices CTAs (Track: one hypothesis would otherwise run on one SM).
-constexpr int kLnMeanSliceHyps = 16, kLnMeanSlices = 8;
+// partial: n * kLnMeanSlices * 512 floats of scratch.  The tokens of a hypothesis are split over
+// kLnMeanSlices CTAs (one hypothesis on one SM took 24 us; at n = 252 one CTA per hypothesis reached 2 TB/s)
+// and a second kernel adds the slices in a fixed order.
+constexpr int kLnMeanSlices = 8;
 void launch_layernorm_mean(const __half* x, const float* gamma, const float* beta, float* out, int n,
                            float* partial, cudaStream_t s);
 // mean over the 400 tokens: x [n,400,512] fp16 -> out [n,512] f32

@@ -85,7 +85,7 @@ Arena::Arena(int max_hyps) : cap(max_hyps) {
       {(void**)&qkv, 3 * tok}, {(void**)&att, tok}, {(void**)&proj, tok}, {(void**)&x1, tok},
       {(void**)&ff1, tok}, {(void**)&ff2, tok}, {(void**)&x2, tok},
       {(void**)&mean_t, n * 512 * 4}, {(void**)&mean_r, n * 512 * 4},
-      {(void**)&mean_part, (size_t)kLnMeanSliceHyps * kLnMeanSlices * 512 * 4},
+      {(void**)&mean_part, (size_t)n * kLnMeanSlices * 512 * 4},
   };
   size_t total = 0;
   for (auto& it : items) total += (it.bytes + 1023) / 1024 * 1024;
@@ -292,8 +292,8 @@ void Network::collect_profile(double* ms, double* flops, long long* launches) {
 }
 
 int Network::launches_per_forward(int n) {
-  // the sliced LayerNorm + mean of the two refiner heads is two kernels per step for few hypotheses
-  return (int)plan(n).steps.size() + (kind_ == NetKind::kRefiner && n <= kLnMeanSliceHyps ? 2 : 0);
+  // the sliced LayerNorm + mean of the two refiner heads is two kernels per step
+  return (int)plan(n).steps.size() + (kind_ == NetKind::kRefiner ? 2 : 0);
 }
 
 }  // namespace fpb

@@ -755,13 +755,15 @@ int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vcl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  bool split = n * kRenderTiles * 4 <= sms;
+  // band kernel: 4 CTAs per hypothesis and 4 resident CTAs per SM; below ~2 CTAs per SM it is bound by the
+  // latency of one CTA walking every triangle (N = 1 and N = 32 take the same ~105 us)
+  bool split = n * kRenderTiles <= 2 * sms;
   if (const char* e = getenv("FPB200_RENDER_SPLIT")) split = e[0] != '0';  // tests run both paths on the same input
   if (split && zbuf_scratch && n <= zbuf_poses) {
     // few hypotheses: spread the triangles over the machine (see raster_split_kernel)
     cudaMemsetAsync(zbuf_scratch, 0xFF, sizeof(unsigned long long) * (size_t)n * kCrop * kCrop, s);
-    const int want = sms / n, have = (mesh.num_faces + kRenderThreads - 1) / kRenderThreads;
-    const int slices = want < have ? (want < 1 ? 1 : want) : have;
+    const int want = (2 * sms + n - 1) / n, have = (mesh.num_faces + kRenderThreads - 1) / kRenderThreads;
+    const int slices = want < have ? want : have;
     raster_split_kernel<<<dim3(slices, n), kRenderThreads, 0, s>>>(mesh, vclip, zbuf_scratch, status);
     constexpr int kShadeRows = 8;
     shade_split_kernel<<<dim3(kCrop / kShadeRows, n), kRenderThreads, 0, s>>>(mesh, aux, vclip, vattr, packed, img0,

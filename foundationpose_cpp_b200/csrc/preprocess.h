@@ -66,7 +66,7 @@ void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float dia
 // `img0 + i`.  vclip / vattr: scratch of n * num_vertices float4 each.  zbuf_scratch (may be null):
 // zbuf_poses * 160 * 160 keys; with n <= zbuf_poses and few enough hypotheses to leave SMs idle the
 // triangles are spread over the whole machine on global z-buffers (identical result).
-constexpr int kSplitRenderPoses = 8;
+constexpr int kSplitRenderPoses = 80;
 // Returns the number of kernels launched.
 int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr,
                    __half* packed, int img0, int32_t* rast_id_debug, int* status,
