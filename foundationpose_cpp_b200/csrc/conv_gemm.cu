@@ -1,6 +1,6 @@
 // tcgen05 implicit-GEMM convolution kernel (see conv_gemm.h).
 //
-// Roles inside one persistent CTA (320 threads, one CTA per SM):
+// Roles inside one persistent CTA (64 + 128 kEpiSets = 320 threads, one CTA per SM):
 //   warp 0         : TMA producer.  Two rings: activation BLOCKS (one per tap group x 64 input
 //                    channels: bh + span tile rows, loaded once and shared by the group's taps) and
 //                    weight stages (one block_n-row tile per tap).
@@ -22,12 +22,19 @@ namespace fpb {
 
 namespace {
 
-constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+// Epilogue warp sets (4 warps each, one per TMEM lane quarter).  Measured with 3 sets (448 threads, 128
+// registers): no gain on any layer shape - the short-K linear layers are not paced by the number of
+// epilogue instruction streams but by shared-memory bandwidth (per 128 x 256 tile and K = 512: 256 KB of
+// TMA writes + 256 KB of MMA operand reads + 256 KB of fp32 staging traffic = 6 k clocks at 128 B/clock
+// against 4 k clocks of MMA).
+constexpr int kEpiSets = 2;
+constexpr int kEpiWarps = 4 * kEpiSets;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
 constexpr int kStageBytesPerWarp = 32 * 32 * 4;         // epilogue staging: 32 rows x 32 fp32 columns
 constexpr int kMaxRing = 8;
 constexpr int kBarrierBytes = 1024;  // mbarriers, TMEM slot, the issuer's K-loop schedule
 constexpr int kSchedMax = 96;        // taps x 64-channel blocks of one tile (per-tap kernels)
-constexpr int kSmemBudget = 232448 - 1024 - 8 * kStageBytesPerWarp - kBarrierBytes;  // for the two rings
+constexpr int kSmemBudget = 232448 - 1024 - kEpiWarps * kStageBytesPerWarp - kBarrierBytes;  // for the two rings
 
 // PAIR = false: independent CTAs.  PAIR = true: CTA pairs issuing ONE tcgen05.mma.cta_group::2 of
 // M = 256: each SM holds (and ingests) its 128 activation rows and only HALF of the weight tile.
@@ -53,7 +60,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const uint32_t a_base = smem_base;                        // [na] activation blocks
   const uint32_t b_base = a_base + p.na * p.a_bytes;        // [nb] weight stages
   const uint32_t stage_base = b_base + p.nb * p.b_stage_bytes;
-  const uint32_t bar_base = stage_base + 8 * kStageBytesPerWarp;
+  const uint32_t bar_base = stage_base + kEpiWarps * kStageBytesPerWarp;
   // barrier layout (8 B each): full[8], empty[8], tfull[4], tempty[4], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxRing + s); };
@@ -77,7 +84,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int s = 0; s < C::kAccStages; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
       // one arrival per epilogue warp working on the tile (PAIR: of both CTAs, on the leader's barrier)
-      ptx::mbar_init(tempty_bar(s), (C::kAltTiles ? 4 : 8) * CS);
+      ptx::mbar_init(tempty_bar(s), (C::kAltTiles ? 4 : kEpiWarps) * CS);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tm_a);
@@ -289,17 +296,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // chunks: conflict-free both ways) and re-reads them with 4 lanes per row: every global
     // load/store instruction then touches 8 rows x 64 contiguous bytes.  The two warps that share a
     // TMEM lane quarter take alternate 32-column chunks.
-    const int ew = warp - 2;       // 0..7
+    const int ew = warp - 2;       // 0..kEpiWarps-1
     const int q = warp & 3;        // TMEM lane quarter this warp may read
-    const int chunk_par = ew >> 2; // which of the alternating chunks
+    const int chunk_par = ew >> 2; // warp set: which of the interleaved chunks (wide tiles) / tiles (narrow)
     const uint32_t stg = stage_base + static_cast<uint32_t>(ew) * kStageBytesPerWarp;
     const int sub = lane >> 2;  // row within a group of 8
     const int seg = lane & 3;   // 8-column segment of the 32-column chunk
     // staging addresses (bytes): write = own row, read = rows i*8+sub
     const uint32_t wr_base = stg + lane * 128;
     const uint32_t rd_sw = static_cast<uint32_t>(sub & 7);
-    constexpr int kItStep = C::kAltTiles ? 2 : 1;     // narrow tiles: this warp set takes every other tile
-    constexpr int kColStep = C::kAltTiles ? 32 : 64;  // ... and all of its columns
+    constexpr int kItStep = C::kAltTiles ? kEpiSets : 1;           // narrow tiles: the sets take tiles in turn
+    constexpr int kColStep = C::kAltTiles ? 32 : 32 * kEpiSets;    // ... and all of their columns
     for (int it = C::kAltTiles ? chunk_par : 0, tile = cluster_id + it * num_clusters; tile < total_tiles;
          tile += kItStep * num_clusters, it += kItStep) {
       const int nt = tile % p.n_tiles;
@@ -679,7 +686,7 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   const long long work = ((m_tiles + cluster - 1) / cluster) * p.n_tiles;  // per cluster
   const int cap = (d.max_ctas > 0 ? d.max_ctas : g_num_sms) / cluster;
   plan->grid = (int)(work < cap ? work : cap) * cluster;
-  plan->smem = 1024 + (size_t)p.na * p.a_bytes + (size_t)p.nb * p.b_stage_bytes + 8 * kStageBytesPerWarp + kBarrierBytes;
+  plan->smem = 1024 + (size_t)p.na * p.a_bytes + (size_t)p.nb * p.b_stage_bytes + kEpiWarps * kStageBytesPerWarp + kBarrierBytes;
   plan->flops = 2.0 * d.n_img * d.out_h * d.out_w * (double)d.cout * d.num_taps * d.cin;
   return nullptr;
 }

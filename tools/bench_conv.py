@@ -33,6 +33,7 @@ def main():
         ("c3 512->512", n, 20, 512, 512, (4, 4, 8), capi.TAPS_3X3_S1),
         ("lin 512->1536", 1, n * 400, 512, 1536, (128, 1, 1), capi.TAPS_1X1),
         ("lin 512->512", 1, n * 400, 512, 512, (128, 1, 1), capi.TAPS_1X1),
+        ("lin 512->512 +res", 1, n * 400, 512, 512, (128, 1, 1), capi.TAPS_1X1),
     ]
     only = os.environ.get("FPB_CASE")
     for ci, (name, imgs, hw, cin, cout, tile, kind) in enumerate(cases):
@@ -67,6 +68,9 @@ def main():
         d.in_, d.n_img, d.out_h, d.out_w = ptr(x), imgs, ho, wo
         d.bw, d.bh, d.bn, d.tap_kind = tile[0], tile[1], tile[2], kind
         d.weight, d.cout, d.bias, d.out, d.relu = ptr(w), cout, ptr(b), ptr(out), 1
+        if name.endswith("+res"):  # out-proj / FFN2 of the encoder layers: residual sum in the epilogue, no ReLU
+            res = torch.randn(hw, cout, device="cuda").half()
+            d.residual, d.res_ld, d.relu = ptr(res), cout, 0
         ms = capi.debug_conv_gemm(d, rep)
         flops = 2.0 * imgs * ho * wo * cout * taps * d.cin
         tf = flops / ms / 1e9
