@@ -387,17 +387,138 @@ __device__ __forceinline__ void setup_pleq(float z0, float z1, float z2, int v0x
   pl[2] = z;
 }
 
+// One snapped (sub)triangle of triangle t inside GL rows [row0, row0 + nrows): cudaraster's depth plane
+// (setupTriangle, TriangleSetup.inl:120-177), exact coverage with its fill rule (Util.inl:304-309) and a
+// 64-bit atomicMin per covered sample on a z-buffer (shared or global memory, row pitch 160) whose key is
+// (u32 depth << 32) | ~triangle: nearest wins and on equal depth the later triangle wins
+// (FineRaster.inl:152-172,338-351), whatever the order in which triangles arrive.  `live` = false makes
+// the call a no-op (callers keep their warps converged instead of branching around it).
+__device__ __forceinline__ void raster_piece(bool live, int p0x, int p0y, int p1x, int p1y, int p2x, int p2y, float z0,
+                                             float z1, float z2, float rw0, float rw1, float rw2, int t, int row0,
+                                             int nrows, unsigned long long* zbuf) {
+  constexpr int W = kCrop, H = kCrop;
+  constexpr int bias = (W - 1) << 3;  // sample x of pixel px = px*16 - bias
+  const int lox = min3(p0x, p1x, p2x), loy = min3(p0y, p1y, p2y);
+  const int hix = max3(p0x, p1x, p2x), hiy = max3(p0y, p1y, p2y);
+  const int px0 = max((lox + bias + 15) >> 4, 0), px1 = min((hix + bias) >> 4, W - 1);
+  const int py0 = max((loy + bias + 15) >> 4, row0), py1 = min((hiy + bias) >> 4, row0 + nrows - 1);
+  if (px0 > px1 || py0 > py1) live = false;  // no sample of this band inside the bounding box
+  int d1x = p1x - p0x, d1y = p1y - p0y, d2x = p2x - p0x, d2y = p2y - p0y;
+  int area = d1x * d2y - d1y * d2x;
+  if (area == 0) live = false;
+  if (live) {
+    if (area < 0) {
+      int ti;
+      float tf;
+      ti = d1x; d1x = d2x; d2x = ti;
+      ti = d1y; d1y = d2y; d2y = ti;
+      ti = p1x; p1x = p2x; p2x = ti;
+      ti = p1y; p1y = p2y; p2y = ti;
+      tf = z1; z1 = z2; z2 = tf;
+      tf = rw1; rw1 = rw2; rw2 = tf;
+      area = -area;
+    }
+    const float zcoef = (float)(kDepthMax - kDepthMin) * 0.5f;
+    const float zbias = (float)(kDepthMax + kDepthMin) * 0.5f;
+    const float zv0 = fmaf(z0 * zcoef, rw0, zbias), zv1 = fmaf(z1 * zcoef, rw1, zbias),
+                zv2 = fmaf(z2 * zcoef, rw2, zbias);
+    unsigned pl[3];
+    setup_pleq(zv0, zv1, zv2, p0x + (W << 3) - 8, p0y + (H << 3) - 8, d1x, d1y, d2x, d2y,
+               1.0f / (float)area, pl);
+    const int e0x = d1x, e0y = d1y, e1x = d2x - d1x, e1y = d2y - d1y, e2x = -d2x, e2y = -d2y;
+    const long long adj0 = (e0y > 0 || (e0y == 0 && e0x <= 0)) ? 1 : 0;
+    const long long adj1 = (e1y > 0 || (e1y == 0 && e1x <= 0)) ? 1 : 0;
+    const long long adj2 = (e2y > 0 || (e2y == 0 && e2x <= 0)) ? 1 : 0;
+    const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - (unsigned)t);
+    for (int py = py0; py <= py1; ++py) {
+      const int sy = py * 16 - bias;
+      for (int px = px0; px <= px1; ++px) {
+        const int sx = px * 16 - bias;
+        const long long v0 = (long long)(p0x - sx) * e0y - (long long)(p0y - sy) * e0x - adj0;
+        const long long v1 = (long long)(p1x - sx) * e1y - (long long)(p1y - sy) * e1x - adj1;
+        const long long v2 = (long long)(p0x - sx) * e2y - (long long)(p0y - sy) * e2x - adj2;
+        if ((v0 | v1 | v2) >= 0) {
+          const unsigned depth = pl[0] * (unsigned)px + pl[1] * (unsigned)py + pl[2];
+          // depth > kDepthMax would lie behind the cleared depth (FineRaster.inl:338)
+          if (depth <= kDepthMax) atomicMin(&zbuf[(py - row0) * W + px], ((unsigned long long)depth << 32) | low);
+        }
+      }
+    }
+  }
+}
+
+// cudaraster's polygon clipper (Util.inl:101-160, TriangleSetup.inl:311-390) for the rare triangle that
+// crosses the near / far plane or leaves the S16 snap range: the triangle is clipped against the frustum
+// planes in barycentric space (Sutherland-Hodgman), the polygon is fan-triangulated, every piece is snapped
+// and rasterised with the triangle's id.  Floating-point contraction is written out the way nvcc compiled it
+// for the reference (this file is built with -fmad=false): a + b*c + d*e = fma(d, e, fma(b, c, a)),
+// x*ac + y*bc = fma(x, ac, y*bc).  Not inlined: its arrays stay out of the fast path's register budget.
+__device__ __forceinline__ int clip_poly_plane(float* out, const float* in, int num_in, float v0, float v1, float v2) {
+  int num_out = 0;
+  if (num_in >= 3) {
+    int ai = (num_in - 1) * 2;
+    float av = fmaf(v2, in[ai + 1], fmaf(v1, in[ai + 0], v0));
+    for (int bi = 0; bi < num_in * 2; bi += 2) {
+      const float bv = fmaf(v2, in[bi + 1], fmaf(v1, in[bi + 0], v0));
+      if (av * bv < 0.0f) {
+        const float bc = av / (av - bv);
+        const float ac = 1.0f - bc;
+        out[num_out + 0] = fmaf(in[ai + 0], ac, in[bi + 0] * bc);
+        out[num_out + 1] = fmaf(in[ai + 1], ac, in[bi + 1] * bc);
+        num_out += 2;
+      }
+      if (bv >= 0.0f) {
+        out[num_out + 0] = in[bi + 0];
+        out[num_out + 1] = in[bi + 1];
+        num_out += 2;
+      }
+      ai = bi;
+      av = bv;
+    }
+  }
+  return num_out >> 1;
+}
+__device__ __noinline__ void raster_clipped(float4 A, float4 B, float4 C, int t, int row0, int nrows,
+                                            unsigned long long* zbuf) {
+  const float a[4] = {A.x, A.y, A.z, A.w};
+  const float d1[4] = {B.x - A.x, B.y - A.y, B.z - A.z, B.w - A.w};
+  const float d2[4] = {C.x - A.x, C.y - A.y, C.z - A.z, C.w - A.w};
+  const float bb[4] = {B.x, B.y, B.z, B.w}, cc[4] = {C.x, C.y, C.z, C.w};
+  float bary[18], temp[18];
+  int num = 3;
+  bary[0] = 0.0f, bary[1] = 0.0f;
+  bary[2] = 1.0f, bary[3] = 0.0f;
+  bary[4] = 0.0f, bary[5] = 1.0f;
+  for (int ax = 0; ax < 3; ++ax) {
+    if ((a[3] < fabsf(a[ax])) | (bb[3] < fabsf(bb[ax])) | (cc[3] < fabsf(cc[ax]))) {
+      num = clip_poly_plane(temp, bary, num, a[3] + a[ax], d1[3] + d1[ax], d2[3] + d2[ax]);
+      num = clip_poly_plane(bary, temp, num, a[3] - a[ax], d1[3] - d1[ax], d2[3] - d2[ax]);
+    }
+  }
+  if (num < 3) return;
+  const float vs = (float)(kCrop << 3);
+  float v0[4], v1[4], v2[4];
+  for (int k = 0; k < 4; ++k) {
+    v0[k] = fmaf(d2[k], bary[1], fmaf(d1[k], bary[0], a[k]));
+    v1[k] = fmaf(d2[k], bary[3], fmaf(d1[k], bary[2], a[k]));
+  }
+  for (int i = 2; i < num; ++i) {
+    for (int k = 0; k < 4; ++k) v2[k] = fmaf(d2[k], bary[i * 2 + 1], fmaf(d1[k], bary[i * 2 + 0], a[k]));
+    const float rw0 = 1.0f / v0[3], rw1 = 1.0f / v1[3], rw2 = 1.0f / v2[3];
+    raster_piece(true, snap(v0[0] * rw0 * vs), snap(v0[1] * rw0 * vs), snap(v1[0] * rw1 * vs), snap(v1[1] * rw1 * vs),
+                 snap(v2[0] * rw2 * vs), snap(v2[1] * rw2 * vs), v0[2], v1[2], v2[2], rw0, rw1, rw2, t, row0, nrows,
+                 zbuf);
+    for (int k = 0; k < 4; ++k) v1[k] = v2[k];
+  }
+}
+
 // Visibility of the triangles t = t_first + i * t_stride (i = 0, 1, ...) inside GL rows [row0, row0 + nrows)
-// of one hypothesis: cudaraster's triangle setup (TriangleSetup.inl fast path) and a 64-bit atomicMin per
-// covered sample on a z-buffer (shared or global memory, row pitch 160) whose key is (u32 depth << 32) |
-// ~triangle, i.e. nearest wins and on equal depth the later triangle wins (FineRaster.inl:152-172,338-351);
-// the result does not depend on the order in which triangles arrive.  Returns whether some triangle would
-// have taken cudaraster's clip path.
+// of one hypothesis: cudaraster's triangle setup (TriangleSetup.inl:181-391; fast path inline, clip path in
+// raster_clipped) and raster_piece per snapped triangle.  Returns whether some triangle took the clip path.
 __device__ __forceinline__ bool raster_triangles(const DeviceMesh& mesh, const float4* __restrict__ pc, int t_first,
                                                  int t_stride, int row0, int nrows, unsigned long long* zbuf) {
-  constexpr int W = kCrop, H = kCrop;
+  constexpr int W = kCrop;
   const float vs = (float)(W << 3);
-  constexpr int bias = (W - 1) << 3;  // sample x of pixel px = px*16 - bias
   bool clip_path = false;
   // Warp-uniform trip count and a single `live` flag instead of `continue`s: the lanes of a warp
   // reconverge at every iteration (with early exits the compiler let them drift apart and the loop
@@ -426,66 +547,25 @@ __device__ __forceinline__ bool raster_triangles(const DeviceMesh& mesh, const f
           ((A.w < +A.z) & (B.w < +B.z) & (C.w < +C.z)) | ((A.w < -A.z) & (B.w < -B.z) & (C.w < -C.z)))
         live = false;
     }
+    bool clipped = false;
     if (live && !((A.w >= fabsf(A.z)) & (B.w >= fabsf(B.z)) & (C.w >= fabsf(C.z)))) {
-      clip_path = true;  // cudaraster would clip this triangle against the near/far plane
+      clipped = true;  // crosses the near / far plane
       live = false;
     }
-    float rw0 = 1.0f / A.w, rw1 = 1.0f / B.w, rw2 = 1.0f / C.w;
-    int p0x = snap(A.x * rw0 * vs), p0y = snap(A.y * rw0 * vs);
-    int p1x = snap(B.x * rw1 * vs), p1y = snap(B.y * rw1 * vs);
-    int p2x = snap(C.x * rw2 * vs), p2y = snap(C.y * rw2 * vs);
-    const int lox = min3(p0x, p1x, p2x), loy = min3(p0y, p1y, p2y);
-    const int hix = max3(p0x, p1x, p2x), hiy = max3(p0y, p1y, p2y);
-    if (live && !(min(lox, loy) >= -32768 && max(hix, hiy) <= 32767 &&
-                  max(hix, hiy) - min(lox, loy) <= (1 << 15) - 1)) {
+    const float rw0 = 1.0f / A.w, rw1 = 1.0f / B.w, rw2 = 1.0f / C.w;
+    const int p0x = snap(A.x * rw0 * vs), p0y = snap(A.y * rw0 * vs);
+    const int p1x = snap(B.x * rw1 * vs), p1y = snap(B.y * rw1 * vs);
+    const int p2x = snap(C.x * rw2 * vs), p2y = snap(C.y * rw2 * vs);
+    const int lo = min(min3(p0x, p1x, p2x), min3(p0y, p1y, p2y));
+    const int hi = max(max3(p0x, p1x, p2x), max3(p0y, p1y, p2y));
+    if (live && !(lo >= -32768 && hi <= 32767 && hi - lo <= (1 << 15) - 1)) {
+      clipped = true;  // outside the S16 snap range / too large for the guard band
+      live = false;
+    }
+    raster_piece(live, p0x, p0y, p1x, p1y, p2x, p2y, A.z, B.z, C.z, rw0, rw1, rw2, t, row0, nrows, zbuf);
+    if (clipped) {
       clip_path = true;
-      live = false;
-    }
-    const int px0 = max((lox + bias + 15) >> 4, 0), px1 = min((hix + bias) >> 4, W - 1);
-    const int py0 = max((loy + bias + 15) >> 4, row0), py1 = min((hiy + bias) >> 4, row0 + nrows - 1);
-    if (px0 > px1 || py0 > py1) live = false;  // no sample of this band inside the bounding box
-    int d1x = p1x - p0x, d1y = p1y - p0y, d2x = p2x - p0x, d2y = p2y - p0y;
-    int area = d1x * d2y - d1y * d2x;
-    if (area == 0) live = false;
-    if (live) {
-      float z0 = A.z, z1 = B.z, z2 = C.z;
-      if (area < 0) {
-        int ti;
-        float tf;
-        ti = d1x; d1x = d2x; d2x = ti;
-        ti = d1y; d1y = d2y; d2y = ti;
-        ti = p1x; p1x = p2x; p2x = ti;
-        ti = p1y; p1y = p2y; p2y = ti;
-        tf = z1; z1 = z2; z2 = tf;
-        tf = rw1; rw1 = rw2; rw2 = tf;
-        area = -area;
-      }
-      const float zcoef = (float)(kDepthMax - kDepthMin) * 0.5f;
-      const float zbias = (float)(kDepthMax + kDepthMin) * 0.5f;
-      const float zv0 = fmaf(z0 * zcoef, rw0, zbias), zv1 = fmaf(z1 * zcoef, rw1, zbias),
-                  zv2 = fmaf(z2 * zcoef, rw2, zbias);
-      unsigned pl[3];
-      setup_pleq(zv0, zv1, zv2, p0x + (W << 3) - 8, p0y + (H << 3) - 8, d1x, d1y, d2x, d2y,
-                 1.0f / (float)area, pl);
-      const int e0x = d1x, e0y = d1y, e1x = d2x - d1x, e1y = d2y - d1y, e2x = -d2x, e2y = -d2y;
-      const long long adj0 = (e0y > 0 || (e0y == 0 && e0x <= 0)) ? 1 : 0;
-      const long long adj1 = (e1y > 0 || (e1y == 0 && e1x <= 0)) ? 1 : 0;
-      const long long adj2 = (e2y > 0 || (e2y == 0 && e2x <= 0)) ? 1 : 0;
-      const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - (unsigned)t);
-      for (int py = py0; py <= py1; ++py) {
-        const int sy = py * 16 - bias;
-        for (int px = px0; px <= px1; ++px) {
-          const int sx = px * 16 - bias;
-          const long long v0 = (long long)(p0x - sx) * e0y - (long long)(p0y - sy) * e0x - adj0;
-          const long long v1 = (long long)(p1x - sx) * e1y - (long long)(p1y - sy) * e1x - adj1;
-          const long long v2 = (long long)(p0x - sx) * e2y - (long long)(p0y - sy) * e2x - adj2;
-          if ((v0 | v1 | v2) >= 0) {
-            const unsigned depth = pl[0] * (unsigned)px + pl[1] * (unsigned)py + pl[2];
-            // depth > kDepthMax would lie behind the cleared depth (FineRaster.inl:338)
-            if (depth <= kDepthMax) atomicMin(&zbuf[(py - row0) * W + px], ((unsigned long long)depth << 32) | low);
-          }
-        }
-      }
+      raster_clipped(A, B, C, t, row0, nrows, zbuf);
     }
     __syncwarp();
   }

@@ -46,7 +46,7 @@ struct DeviceMesh {
 // status word bits written by the sampler
 constexpr int kStatusEmptyMask = 1;
 constexpr int kStatusNoDepth = 2;
-constexpr int kStatusClipPath = 4;  // some triangle needed cudaraster's clip path (dropped)
+constexpr int kStatusClipPath = 4;  // informational: some triangle took cudaraster's polygon clipper
 
 void launch_depth_to_xyz(const float* depth, float* xyz, int h, int w, const Intrinsics& K,
                          cudaStream_t s);

@@ -308,7 +308,7 @@ def build_c_oracle(force: bool = False) -> Path:
 
 def rasterize_ids(clip, faces, h=CROP, w=CROP):
     """cudaraster visibility (oracle/raster_oracle.c).  Returns (ids [h,w] i32 with row 0 = GL
-    bottom row, number of triangles that would have needed cudaraster's clip path)."""
+    bottom row, number of triangles that took cudaraster's polygon clipper)."""
     global _RASTER_LIB
     if _RASTER_LIB is None:
         _RASTER_LIB = ctypes.CDLL(str(build_c_oracle()))

@@ -1,6 +1,7 @@
 """Generates tests/golden/ref_kernels_golden.npz by running the REFERENCE's own CUDA kernels
 (oracle/_ref/libref_kernels.so, built from /root/reference by oracle/Makefile) on seeded inputs.
 Run on a GPU box:   python tests/golden/make_golden.py gpurun_out/ref_kernels_golden.npz
+                    python tests/golden/make_golden.py clip gpurun_out/ref_clip_golden.npz
 The inputs are stored next to the outputs so the CPU oracle can be checked without a GPU."""
 import ctypes as C
 import os
@@ -46,6 +47,39 @@ def golden_inputs():
             "K": np.asarray(K, np.float32)}
 
 
+def clip_inputs():
+    """Hypotheses so close to the camera that the mesh crosses the near plane (z = 0.1 m) or reaches behind
+    the camera (w < 0): every such triangle takes cudaraster's polygon clipper (TriangleSetup.inl:303-390)."""
+    mesh = synth.uv_ellipsoid("g", slices=24, stacks=13, tex_size=64, seed=5)
+    _, _, _, gt = synth.make_scene(mesh)
+    om = helpers.oracle_mesh(mesh)
+    K = synth.DEFAULT_K
+    poses = []
+    for tx, ty, tz in [(0.01, -0.01, 0.14), (-0.02, 0.01, 0.11), (0.0, 0.0, 0.04)]:
+        p = gt.copy()
+        p[:3, 3] = (tx, ty, tz)
+        poses.append(p)
+    poses = np.stack(poses).astype(np.float32)
+    tfs, _ = O.crop_window_tf(poses, K, 1.2, om["diameter"])
+    bbox = O.bbox2d_from_tf(tfs)
+    clip = np.stack([O.clip_vertices(om["vertices"], poses[i], bbox[i], K, 480, 640) for i in range(len(poses))])
+    return {"clip_near": clip.astype(np.float32), "faces": om["faces"], "poses_near": poses}
+
+
+def main_clip(out_path):
+    """tests/golden/ref_clip_golden.npz: cudaraster's visibility ids for clip_inputs()."""
+    lib = ref_lib()
+    g = clip_inputs()
+    n, v, _ = g["clip_near"].shape
+    t = g["faces"].shape[0]
+    clip_d, tri_d = dev(g["clip_near"]), dev(g["faces"])  # keep the device copies alive across the call
+    rast_d = torch.zeros(n, 160, 160, 4, device="cuda")
+    assert lib.ref_rasterize(ptr(clip_d), ptr(tri_d), ptr(rast_d), v, t, 160, 160, n) == 0
+    ids = rast_d[..., 3].cpu().numpy().astype(np.int16)
+    np.savez_compressed(out_path, **g, ref_ids_near=ids)
+    print("wrote", out_path, os.path.getsize(out_path), "bytes; coverage", float((ids > 0).mean()))
+
+
 def main(out_path):
     lib = ref_lib()
     g = golden_inputs()
@@ -86,4 +120,7 @@ def main(out_path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", "ref_kernels_golden.npz"))
+    if len(sys.argv) > 2 and sys.argv[1] == "clip":
+        main_clip(sys.argv[2])
+    else:
+        main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", "ref_kernels_golden.npz"))

@@ -20,6 +20,19 @@ def test_visibility_ids_identical_to_cudaraster():
     assert (G["ref_ids"] > 0).mean() > 0.2
 
 
+def test_polygon_clipper_identical_to_cudaraster():
+    """tests/golden/ref_clip_golden.npz (make_golden.py clip): hypotheses so close that the mesh crosses the
+    near plane / reaches behind the camera, rasterised by the reference's cudaraster on a B200.  The oracle's
+    restatement of its polygon clipper (TriangleSetup.inl:303-390, Util.inl:101-160) must give the same ids."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_clip_golden.npz"))
+    took = 0
+    for i in range(g["clip_near"].shape[0]):
+        ids, nclip = O.rasterize_ids(g["clip_near"][i], g["faces"])
+        took += nclip
+        assert np.array_equal(ids, g["ref_ids_near"][i].astype(np.int32)), f"image {i}"
+    assert took > 50 and (g["ref_ids_near"] > 0).mean() > 0.2
+
+
 def test_shader_interpolate_texture_match_nvdiffrast():
     for i in range(G["clip"].shape[0]):
         ids = G["ref_ids"][i].astype(np.int32)

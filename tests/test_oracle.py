@@ -106,10 +106,19 @@ def test_raster_two_triangles_fill_rule_and_depth():
     v3 = np.array([[0, 0, 0, 1], [0, 0, 0, 1], [0.1, 0.1, 0, 1], [2, 2, 0, 1], [3, 2, 0, 1], [2, 3, 0, 1]], F)
     ids3, _ = O.rasterize_ids(v3, np.array([[0, 1, 2], [3, 4, 5]], np.int32), 16, 16)
     assert ids3.sum() == 0
-    # a triangle crossing the near plane takes cudaraster's clip path (not restated): dropped and counted
+    # a triangle crossing the near plane takes cudaraster's polygon clipper: the part with z/w >= -1 is
+    # drawn.  Vertices (0,0,0), (0.5,0,-2), (0,0.5,0): z = -4x, so the kept part is x <= 0.25.
     v4 = np.array([[0, 0, 0, 1], [0.5, 0, -2, 1], [0, 0.5, 0, 1]], F)
-    _, nclip4 = O.rasterize_ids(v4, np.array([[0, 1, 2]], np.int32), 16, 16)
+    ids4, nclip4 = O.rasterize_ids(v4, np.array([[0, 1, 2]], np.int32), 16, 16)
     assert nclip4 == 1
+    ys, xs = np.nonzero(ids4)
+    cx = (xs + 0.5) / 8 - 1  # NDC x of the covered pixel centres
+    assert len(xs) > 0 and cx.max() <= 0.25 and cx.min() >= 0
+    # the unclipped triangle (same footprint, z inside the range) covers strictly more
+    v5 = v4.copy()
+    v5[1, 2] = 0
+    ids5, nclip5 = O.rasterize_ids(v5, np.array([[0, 1, 2]], np.int32), 16, 16)
+    assert nclip5 == 0 and (ids5 > 0).sum() > (ids4 > 0).sum() and ((ids4 > 0) <= (ids5 > 0)).all()
 
 
 def test_barycentrics_and_interpolate():

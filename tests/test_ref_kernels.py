@@ -85,3 +85,43 @@ def test_product_raster_matches_reference_cudaraster(tmp_path):
     diff = int((got != ref_ids).sum())
     assert diff == 0, f"{diff} of {got.size} visibility ids differ from the reference cudaraster"
     model.close()
+
+
+def test_polygon_clipper_matches_reference_cudaraster(tmp_path):
+    """Hypotheses whose mesh crosses the near plane / reaches behind the camera: the oracle's and the product's
+    restatement of cudaraster's polygon clipper against cudaraster itself.  Bar: identical visibility ids."""
+    import fp_helpers as helpers
+    from foundationpose_cpp_b200 import api, synth
+    from oracle import fp_oracle as O
+    mk = _mk()
+    out = str(tmp_path / "c.npz")
+    mk.main_clip(out)
+    g = np.load(out)
+    n = g["clip_near"].shape[0]
+    ref = g["ref_ids_near"].astype(np.int32)
+    assert (ref > 0).mean() > 0.2
+    took = 0
+    for i in range(n):
+        ids, nclip = O.rasterize_ids(g["clip_near"][i], g["faces"])
+        took += nclip
+        d = int((ids != ref[i]).sum())
+        assert d == 0, f"oracle: image {i}: {d} visibility ids differ from cudaraster ({nclip} clipped triangles)"
+    assert took > 50, "the scene must exercise the clipper"
+    # product kernels (both render paths) on the same hypotheses
+    mesh = synth.uv_ellipsoid("g", slices=24, stacks=13, tex_size=64, seed=5)
+    rgb, depth, mask, gt = synth.make_scene(mesh)
+    rp, sp = helpers.write_seeded_weights(str(tmp_path))
+    model = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], synth.DEFAULT_K, 480, 640)
+    model.upload(rgb, depth)
+    for split in ("0", "1"):
+        os.environ["FPB200_RENDER_SPLIT"] = split
+        try:
+            model.set_hypotheses(g["poses_near"], "g")
+            model.render_and_transform(1.2)
+        finally:
+            del os.environ["FPB200_RENDER_SPLIT"]
+        got = model.read_buffer("rast_id", np.int32, n * 160 * 160).reshape(n, 160, 160)
+        d = int((got != ref).sum())
+        assert d == 0, f"product (split={split}): {d} visibility ids differ from cudaraster"
+        assert model.read_buffer("status", np.int32, 1)[0] & 4, "the clip-path flag must be raised"
+    model.close()
