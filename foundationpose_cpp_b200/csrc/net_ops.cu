@@ -96,49 +96,62 @@ layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
 __global__ void __launch_bounds__(512)
 layernorm_mean_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float* __restrict__ out, float* __restrict__ partial) {
+  // The 400 tokens of a hypothesis are always summed as kLnMeanSlices slices of 50 (warp w of a slice takes
+  // tokens w, w + 16, ... of the slice; the 16 warp sums are added in warp order; the slice sums are added in
+  // slice order), so the result does not depend on how many hypotheses share the launch.  What varies is
+  // how many CTAs share the slices: gridDim.y = 1 (many hypotheses: this CTA does all slices and the final
+  // sum) up to kLnMeanSlices (Track: one slice per CTA, layernorm_mean_combine_kernel adds them).
   __shared__ float part[16][kDim];
+  __shared__ float slice_sum[kLnMeanSlices][kDim];
   const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // gridDim.y > 1 (few hypotheses, Track): this CTA takes a slice of the tokens and leaves an unscaled
-  // partial sum for layernorm_mean_combine_kernel
-  const int per = (kTok + gridDim.y - 1) / gridDim.y;
-  const int t_begin = blockIdx.y * per, t_end = min(kTok, t_begin + per);
-  float g[16], b[16], acc[16];
+  constexpr int kPer = kTok / kLnMeanSlices;
+  const int per_cta = kLnMeanSlices / gridDim.y;
+  float g[16], b[16];
   load_affine16(gamma, beta, lane, g, b);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   const long long row0 = static_cast<long long>(n) * kTok;
-  for (int t = t_begin + warp; t < t_end; t += 32) {
-    float v0[16], v1[16];
-    const bool two = t + 16 < t_end;
-    load_row16(x, row0 + t, lane, v0);
-    if (two) load_row16(x, row0 + t + 16, lane, v1);
-    normalise_row16(v0, g, b);
+  for (int sl = blockIdx.y * per_cta; sl < (blockIdx.y + 1) * per_cta; ++sl) {
+    const int t_begin = sl * kPer, t_end = t_begin + kPer;
+    float acc[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] += v0[i];
-    if (two) {
-      normalise_row16(v1, g, b);
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int t = t_begin + warp; t < t_end; t += 32) {
+      float v0[16], v1[16];
+      const bool two = t + 16 < t_end;
+      load_row16(x, row0 + t, lane, v0);
+      if (two) load_row16(x, row0 + t + 16, lane, v1);
+      normalise_row16(v0, g, b);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] += v1[i];
+      for (int i = 0; i < 16; ++i) acc[i] += v0[i];
+      if (two) {
+        normalise_row16(v1, g, b);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] += v1[i];
+      }
     }
-  }
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) part[warp][h * 256 + lane * 8 + e] = acc[h * 8 + e];
-  __syncthreads();
-  {
-    float s = 0.f;
+      for (int e = 0; e < 8; ++e) part[warp][h * 256 + lane * 8 + e] = acc[h * 8 + e];
+    __syncthreads();
+    float sum = 0.f;
 #pragma unroll 8
-    for (int w = 0; w < 16; ++w) s += part[w][threadIdx.x];
-    if (gridDim.y == 1) out[static_cast<long long>(n) * kDim + threadIdx.x] = s * (1.f / kTok);
-    else partial[(static_cast<long long>(n) * gridDim.y + blockIdx.y) * kDim + threadIdx.x] = s;
+    for (int w = 0; w < 16; ++w) sum += part[w][threadIdx.x];
+    if (gridDim.y == 1) slice_sum[sl][threadIdx.x] = sum;
+    else partial[(static_cast<long long>(n) * kLnMeanSlices + sl) * kDim + threadIdx.x] = sum;
+    __syncthreads();  // part[] is rewritten by the next slice
+  }
+  if (gridDim.y == 1) {
+    float sum = 0.f;
+    for (int k = 0; k < kLnMeanSlices; ++k) sum += slice_sum[k][threadIdx.x];
+    out[static_cast<long long>(n) * kDim + threadIdx.x] = sum * (1.f / kTok);
   }
 }
 __global__ void __launch_bounds__(512)
-layernorm_mean_combine_kernel(const float* __restrict__ partial, float* __restrict__ out, int slices) {
-  float s = 0.f;
-  for (int k = 0; k < slices; ++k) s += partial[(static_cast<long long>(blockIdx.x) * slices + k) * kDim + threadIdx.x];
-  out[static_cast<long long>(blockIdx.x) * kDim + threadIdx.x] = s * (1.f / kTok);
+layernorm_mean_combine_kernel(const float* __restrict__ partial, float* __restrict__ out) {
+  float sum = 0.f;
+  for (int k = 0; k < kLnMeanSlices; ++k)
+    sum += partial[(static_cast<long long>(blockIdx.x) * kLnMeanSlices + k) * kDim + threadIdx.x];
+  out[static_cast<long long>(blockIdx.x) * kDim + threadIdx.x] = sum * (1.f / kTok);
 }
 
 // One 1024-thread CTA per hypothesis: four groups of 256 threads each sum 100 tokens (one coalesced
@@ -435,13 +448,16 @@ void launch_layernorm(const __half* x, const float* gamma, const float* beta, __
   layernorm_kernel<<<(unsigned)blocks, threads, 0, s>>>(x, gamma, beta, out, rows);
 }
 
-void launch_layernorm_mean(const __half* x, const float* gamma, const float* beta, float* out, int n,
-                           float* partial, cudaStream_t s) {
-  if (n <= 0) return;
-  // always kLnMeanSlices token slices per hypothesis, whatever n: the summation order (and so the result)
-  // does not depend on how many hypotheses share the launch (sharded == unsharded, Track == Register)
-  layernorm_mean_kernel<<<dim3(n, kLnMeanSlices), 512, 0, s>>>(x, gamma, beta, out, partial);
-  layernorm_mean_combine_kernel<<<n, 512, 0, s>>>(partial, out, kLnMeanSlices);
+int launch_layernorm_mean(const __half* x, const float* gamma, const float* beta, float* out, int n,
+                          float* partial, cudaStream_t s) {
+  if (n <= 0) return 0;
+  // CTAs per hypothesis: enough to fill the machine, never more than the slices
+  int split = 1;
+  while (split < kLnMeanSlices && n * split < 128) split *= 2;
+  layernorm_mean_kernel<<<dim3(n, split), 512, 0, s>>>(x, gamma, beta, out, partial);
+  if (split == 1) return 1;
+  layernorm_mean_combine_kernel<<<n, 512, 0, s>>>(partial, out);
+  return 2;
 }
 
 void launch_token_mean(const __half* x, float* out, int n, cudaStream_t s) {

@@ -17,13 +17,13 @@ bool attention_phase_clocks(unsigned long long out[22]);
 void launch_layernorm(const __half* x, const float* gamma, const float* beta, __half* out, long long rows,
                       cudaStream_t s);
 // out[n,512] f32 = mean over the 400 tokens of LayerNorm(x[n,400,512]); the normalised tokens are not stored.
-// partial: n * kLnMeanSlices * 512 floats of scratch.  The tokens of a hypothesis are split over
-// kLnMeanSlices CTAs (one hypothesis on one SM took 24 us; at n = 252 one CTA per hypothesis reached 2 TB/s)
-// and a second kernel adds the slices in a fixed order.
+// partial: n * kLnMeanSlices * 512 floats of scratch.  The tokens of a hypothesis are always summed as
+// kLnMeanSlices slices in a fixed order (the result does not depend on n); with few hypotheses the slices
+// are spread over up to kLnMeanSlices CTAs and a second kernel adds them (one hypothesis on one SM took
+// 24 us).  Returns the number of kernels launched.
 constexpr int kLnMeanSlices = 8;
-void launch_layernorm_mean(const __half* x, const float* gamma, const float* beta, float* out, int n,
-                           float* partial, cudaStream_t s);
-// mean over the 400 tokens: x [n,400,512] fp16 -> out [n,512] f32
+int launch_layernorm_mean(const __half* x, const float* gamma, const float* beta, float* out, int n,
+                          float* partial, cudaStream_t s);
 void launch_token_mean(const __half* x, float* out, int n, cudaStream_t s);
 // out[r,o] = sum_k in[r,k] * w[o,k] + b[o]   (fp32, small shapes)
 void launch_small_linear(const float* in, const float* w, const float* b, float* out, int rows, int k,

@@ -292,8 +292,8 @@ void Network::collect_profile(double* ms, double* flops, long long* launches) {
 }
 
 int Network::launches_per_forward(int n) {
-  // the sliced LayerNorm + mean of the two refiner heads is two kernels per step
-  return (int)plan(n).steps.size() + (kind_ == NetKind::kRefiner ? 2 : 0);
+  // the LayerNorm + token mean of the two refiner heads is two kernels per step for few hypotheses
+  return (int)plan(n).steps.size() + (kind_ == NetKind::kRefiner && n < 128 ? 2 : 0);
 }
 
 }  // namespace fpb

@@ -564,8 +564,11 @@ __device__ __forceinline__ bool raster_triangles(const DeviceMesh& mesh, const f
     }
     raster_piece(live, p0x, p0y, p1x, p1y, p2x, p2y, A.z, B.z, C.z, rw0, rw1, rw2, t, row0, nrows, zbuf);
     if (clipped) {
+      // rare: the vertices are fetched again here (through a different load path, so that the compiler cannot
+      // keep the 12 floats above alive across the pixel loop of the fast path)
       clip_path = true;
-      raster_clipped(A, B, C, t, row0, nrows, zbuf);
+      const int j0 = __ldcg(mesh.faces + 3 * t), j1 = __ldcg(mesh.faces + 3 * t + 1), j2 = __ldcg(mesh.faces + 3 * t + 2);
+      raster_clipped(__ldcg(pc + j0), __ldcg(pc + j1), __ldcg(pc + j2), t, row0, nrows, zbuf);
     }
     __syncwarp();
   }
