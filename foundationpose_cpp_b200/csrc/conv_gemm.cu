@@ -361,6 +361,51 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       // overlaps the arithmetic and stores of chunk c.
       uint32_t r[32];
       ptx::tmem_ld_32x32b_x32(taddr + c_first, r);
+      if (!res16 && !p.post_add) {
+        // No residual sum and no positional table (the QKV / FFN1 linear layers and half of the convolutions):
+        // bias and ReLU are applied in the accumulator's own layout (a thread owns a row, the 32 bias values are
+        // broadcast loads) and the chunk is staged as fp16 - half the shared-memory traffic of the fp32
+        // transpose below, which is what paces the short-K layers.  Same fp32 operations, same rounding.
+        const float* brow = p.bias + nt * BN;
+        const uint32_t wr16 = stg + lane * 64;
+        const uint32_t wr_sw = static_cast<uint32_t>((lane >> 1) & 3);
+#pragma unroll 1
+        for (int c0 = c_first; c0 < BN; c0 += kColStep) {
+          float4 bb[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(brow + c0) + j);
+          ptx::tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v0 = __uint_as_float(r[4 * j + 0]) + bb[j].x, v1 = __uint_as_float(r[4 * j + 1]) + bb[j].y;
+            float v2 = __uint_as_float(r[4 * j + 2]) + bb[j].z, v3 = __uint_as_float(r[4 * j + 3]) + bb[j].w;
+            if (p.relu) {
+              v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+            }
+            const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+            pk[2 * j] = *reinterpret_cast<const uint32_t*>(&h01);
+            pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+          }
+          if (c0 + kColStep < BN) ptx::tmem_ld_32x32b_x32(taddr + c0 + kColStep, r);
+          // 64-byte rows, 16-byte units XOR-swizzled by (row / 2) % 4: conflict-free for the row-per-lane
+          // writes and for the 4-lanes-per-row reads
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            ptx::st_shared_v4(wr16 + ((c ^ wr_sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + sub;
+            float f0, f1, f2, f3;
+            ptx::ld_shared_v4(stg + row * 64 + ((seg ^ ((row >> 1) & 3)) << 4), f0, f1, f2, f3);
+            if ((vmask >> i) & 1u)
+              out16[out_off[i] + (c0 >> 3)] = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2),
+                                                         __float_as_uint(f3));
+          }
+          __syncwarp();
+        }
+      } else
 #pragma unroll 1
       for (int c0 = c_first; c0 < BN; c0 += kColStep) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr + c0));
