@@ -832,12 +832,12 @@ int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vcl
                   cudaStream_t s) {
   if (n <= 0) return 0;
   vertex_stage_kernel<<<dim3((mesh.num_vertices + 255) / 256, n), 256, 0, s>>>(mesh, aux, vclip, vattr);
-  int sms = 148;
-  {
-    int dev = 0;
+  static const int sms = [] {
+    int dev = 0, n = 148;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
   // band kernel: 4 CTAs per hypothesis and 4 resident CTAs per SM; below ~2 CTAs per SM it is bound by the
   // latency of one CTA walking every triangle (N = 1 and N = 32 take the same ~105 us)
   bool split = n * kRenderTiles <= 2 * sms;
