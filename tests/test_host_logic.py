@@ -215,3 +215,22 @@ def test_weight_importers_pth_and_onnx(tmp_path):
         got = weights.read_weight_file(str(out))
         for k in want:
             np.testing.assert_allclose(got[k].astype(np.float32), want[k].astype(np.float32), rtol=2e-3, atol=1e-6)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU restatement timed as the reference arm): one JSON line with the
+    contract's keys; no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["unit"] == "hyp/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("Register pose-hypotheses/sec") and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    for k in ("n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in d, k

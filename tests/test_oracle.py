@@ -220,3 +220,37 @@ def test_oracle_render_agrees_with_independent_raycast():
     assert np.median(np.abs(ren[0][inner][:, :3] - tra[0][inner][:, :3])) < 0.03     # colours
     valid = inner & (tra[0][..., 5] != 0)
     assert np.median(np.abs(ren[0][valid][:, 3:] - tra[0][valid][:, 3:])) < 0.03     # normalised xyz (3 mm / radius)
+
+
+def test_clipper_agrees_with_double_precision_clipping():
+    """Property: a triangle that crosses the near plane, rasterised through the restated cudaraster clipper
+    (fp32, barycentric Sutherland-Hodgman), covers the same pixels as the polygon obtained by clipping it in
+    float64 and fan-triangulating it by hand - up to a few boundary pixels along the cut, where the two
+    paths round differently."""
+    rng = np.random.default_rng(11)
+    W = H = 64
+    worst = 0
+    drawn = 0
+    for _ in range(40):
+        # two vertices inside the depth range, one in front of the near plane (z/w < -1)
+        v = np.zeros((3, 4), np.float64)
+        v[:, 3] = rng.uniform(0.5, 2.0, 3)
+        v[:, 0] = rng.uniform(-0.8, 0.8, 3) * v[:, 3]
+        v[:, 1] = rng.uniform(-0.8, 0.8, 3) * v[:, 3]
+        v[:2, 2] = rng.uniform(-0.8, 0.8, 2) * v[:2, 3]
+        v[2, 2] = -rng.uniform(1.2, 3.0) * v[2, 3]
+        ids, nclip = O.rasterize_ids(v.astype(F), np.array([[0, 1, 2]], np.int32), H, W)
+        assert nclip == 1
+        # float64 clip against w + z >= 0: the two crossing edges are 0-2 and 1-2
+        d = v[:, 3] + v[:, 2]
+        cut = [v[k] + (v[2] - v[k]) * (d[k] / (d[k] - d[2])) for k in (0, 1)]
+        poly = np.array([v[0], v[1], cut[1], cut[0]])
+        # pull the cut vertices a hair inside the range so that they take the fast path
+        poly[2:, 2] = np.maximum(poly[2:, 2], -poly[2:, 3] * (1 - 1e-6))
+        ids2, nclip2 = O.rasterize_ids(poly.astype(F), np.array([[0, 1, 2], [0, 2, 3]], np.int32), H, W)
+        assert nclip2 == 0
+        diff = int(((ids > 0) != (ids2 > 0)).sum())
+        worst = max(worst, diff)
+        drawn += int((ids > 0).sum())
+        assert diff <= 0.02 * max(1, (ids2 > 0).sum()) + 3, diff
+    assert drawn > 2000, "the random triangles must cover something"
