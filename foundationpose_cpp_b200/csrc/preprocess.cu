@@ -313,9 +313,11 @@ __global__ void pose_setup_kernel(const float* __restrict__ poses, int n, Intrin
 }
 
 // ------------------------------------------------------------------ render
-constexpr int kRenderThreads = 256;
-constexpr int kRenderTiles = 4;                      // horizontal bands per hypothesis
-constexpr int kTileRows = kCrop / kRenderTiles;      // 40 rows -> 51 KB z-buffer, 4 CTAs per SM
+constexpr int kRenderThreads = 256;                  // split-path kernels
+constexpr int kBandThreads = 512;                    // band kernel
+constexpr int kRenderTiles = 2;                      // horizontal bands per hypothesis: every band CTA walks all
+                                                     // triangles, so fewer, larger bands repeat less set-up work
+constexpr int kTileRows = kCrop / kRenderTiles;      // 80 rows -> 102 KB z-buffer, 2 CTAs (32 warps) per SM
 constexpr unsigned kDepthMin = 2200u << 3;
 constexpr unsigned kDepthMax = 0xFFFFFFFFu - (2200u << 3);
 
@@ -667,7 +669,7 @@ __device__ __forceinline__ void shade_pixels(const DeviceMesh& mesh, const PoseA
 
 // One CTA per (band of 40 rows, hypothesis): every thread takes triangles and resolves visibility on a
 // shared-memory z-buffer (raster_triangles), then the band is shaded (shade_pixels).
-__global__ void __launch_bounds__(kRenderThreads, 4)
+__global__ void __launch_bounds__(kBandThreads, 2)
 render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vclip,
               const float4* __restrict__ vattr, __half* __restrict__ packed, int img0,
               int32_t* __restrict__ rast_id_debug, int* __restrict__ status) {
@@ -840,7 +842,7 @@ int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vcl
   }();
   // band kernel: 4 CTAs per hypothesis and 4 resident CTAs per SM; below ~2 CTAs per SM it is bound by the
   // latency of one CTA walking every triangle (N = 1 and N = 32 take the same ~105 us)
-  bool split = n * kRenderTiles <= 2 * sms;
+  bool split = n * 4 <= 2 * sms;
   if (const char* e = getenv("FPB200_RENDER_SPLIT")) split = e[0] != '0';  // tests run both paths on the same input
   if (split && zbuf_scratch && n <= zbuf_poses) {
     // few hypotheses: spread the triangles over the machine (see raster_split_kernel)
@@ -853,7 +855,7 @@ int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vcl
                                                                              rast_id_debug, zbuf_scratch, kShadeRows);
     return 3;
   }
-  render_kernel<<<dim3(kRenderTiles, n), kRenderThreads, kCrop * kTileRows * 8, s>>>(mesh, aux, vclip, vattr, packed,
+  render_kernel<<<dim3(kRenderTiles, n), kBandThreads, kCrop * kTileRows * 8, s>>>(mesh, aux, vclip, vattr, packed,
                                                                                       img0, rast_id_debug, status);
   return 2;
 }
