@@ -90,12 +90,17 @@ def main(out_path):
     rast_d = torch.zeros(n, H, W, 4, device="cuda")
     assert lib.ref_rasterize(ptr(clip_d), ptr(tri_d), ptr(rast_d), v, t, H, W, n) == 0
     xyz_d = torch.zeros(n, H, W, 3, device="cuda")
-    assert lib.ref_interpolate(ptr(dev(g["pts_cam"])), ptr(rast_d), ptr(tri_d), ptr(xyz_d), v, t, 3, 3, H, W, n) == 0
+    # every device copy is bound to a name for the duration of the call: a temporary would be released as soon
+    # as its pointer has been taken, and a second temporary in the same expression may then reuse its memory
+    pts_d = dev(g["pts_cam"])
+    assert lib.ref_interpolate(ptr(pts_d), ptr(rast_d), ptr(tri_d), ptr(xyz_d), v, t, 3, 3, H, W, n) == 0
     uv_d = torch.zeros(n, H, W, 2, device="cuda")
-    assert lib.ref_interpolate(ptr(dev(g["texcoords"])), ptr(rast_d), ptr(tri_d), ptr(uv_d), v, t, 2, 2, H, W, n) == 0
+    tc_d = dev(g["texcoords"])
+    assert lib.ref_interpolate(ptr(tc_d), ptr(rast_d), ptr(tri_d), ptr(uv_d), v, t, 2, 2, H, W, n) == 0
     col_d = torch.zeros(n, H, W, 3, device="cuda")
     th, tw, _ = g["texture"].shape
-    assert lib.ref_texture(ptr(dev(g["texture"])), ptr(uv_d), ptr(col_d), th, tw, H, W, n) == 0
+    tex_d = dev(g["texture"])
+    assert lib.ref_texture(ptr(tex_d), ptr(uv_d), ptr(col_d), th, tw, H, W, n) == 0
     dp = dev(g["depth_patch"])
     er, fl = torch.zeros_like(dp), torch.zeros_like(dp)
     assert lib.ref_depth_filters(ptr(dp), ptr(er), ptr(fl), dp.shape[0], dp.shape[1]) == 0
@@ -106,7 +111,8 @@ def main(out_path):
     assert lib.ref_depth_to_xyz(ptr(dp), ptr(xyzm), dp.shape[0], dp.shape[1], float(K[0, 0]), float(K[1, 1]),
                                 float(K[0, 2]), float(K[1, 2]), 0.001) == 0
     scores = np.array([0.1, 0.9, -0.3, 0.9, 0.5], np.float32)
-    best = lib.ref_argmax(ptr(dev(scores)), len(scores))
+    scores_d = dev(scores)
+    best = lib.ref_argmax(ptr(scores_d), len(scores))
     rast = rast_d.cpu().numpy()
     sub = (slice(None), slice(0, H, 4), slice(0, W, 4))
     np.savez_compressed(
