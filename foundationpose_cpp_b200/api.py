@@ -157,7 +157,8 @@ class FoundationPose:
             return False, None
         out = np.zeros(16, np.float32)
         h, w = depth.shape
-        ok = self._ok(self._lib.fpb200_register(self._h, _fptr(rgb), _fptr(depth), _fptr(mask), h, w,
+        # mask=None: reuse the mask already resident on the device (fails with "mask must not be null" if none is)
+        ok = self._ok(self._lib.fpb200_register(self._h, _fptr(rgb), _fptr(depth), _fptr(mask) if mask is not None else None, h, w,
                                                  target_name.encode(), int(refine_itr), _fptr(out)))
         return ok, (out.reshape(4, 4).T.copy() if ok else None)
 
@@ -245,6 +246,10 @@ class FoundationPose:
         raw = self.read_buffer(which, np.float16, n * CROP * STEM_PITCH * PACK_C)
         return raw.reshape(n, CROP, STEM_PITCH, PACK_C)[:, :, STEM_PAD:, :6].astype(np.float32)
 
+    def debug_options(self, rast_ids: bool = False, render_split: int = -1):
+        """Test switches (fpb200_debug_options): write the visibility id map, force a render path."""
+        capi.check(self._lib.fpb200_debug_options(self._h, int(bool(rast_ids)), int(render_split)))
+
     def last_timings(self) -> List[float]:
         ms = (C.c_float * 8)()
         n = self._lib.fpb200_last_timings(self._h, ms, 8)
@@ -283,6 +288,20 @@ class FoundationPose:
         capi.check(self._lib.fpb200_wait(self._h, C.byref(idx), _fptr(out)))
         return idx.value, out.reshape(4, 4).T.copy()
 
+    # ---- multi-GPU exchange over peer memory (fpb200_exchange_*) -----------------------------
+    def exchange_export(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this rank's exchange region."""
+        buf = (C.c_ubyte * capi.IPC_HANDLE_BYTES)()
+        capi.check(self._lib.fpb200_exchange_export(self._h, buf))
+        return bytes(buf)
+
+    def exchange_connect(self, handles: Sequence[bytes]):
+        """handles: the exported handle of every rank, in rank order (this rank's own entry is ignored)."""
+        if len(handles) != self.shard_world or any(len(h) != capi.IPC_HANDLE_BYTES for h in handles):
+            raise ValueError(f"need {self.shard_world} handles of {capi.IPC_HANDLE_BYTES} bytes")
+        blob = b"".join(handles)
+        capi.check(self._lib.fpb200_exchange_connect(self._h, (C.c_ubyte * len(blob)).from_buffer_copy(blob)))
+
     def set_gemm_profile(self, on: bool):
         capi.check(self._lib.fpb200_set_gemm_profile(self._h, int(bool(on))))
 
@@ -290,6 +309,12 @@ class FoundationPose:
         ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
         capi.check(self._lib.fpb200_gemm_profile(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
         return ms.value, fl.value, n.value
+
+
+def connect_local(models: Sequence[FoundationPose]):
+    """Wire the exchange of `world` sharded sessions that live in this process (rank order)."""
+    arr = (C.c_void_p * len(models))(*[m._h for m in models])
+    capi.check(capi.lib().fpb200_exchange_connect_local(arr, len(models)))
 
 
 def CreateFoundationPoseModel(refiner_weights: str, scorer_weights: str, mesh_loaders, K, max_h: int = 1080,

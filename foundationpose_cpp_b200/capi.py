@@ -16,6 +16,7 @@ class FpbError(RuntimeError):
 
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_STATE, ERR_NO_DEPTH = 0, -1, -2, -3, -4, -5
 TAPS_1X1, TAPS_3X3_S1, TAPS_3X3_S2_PHASE, TAPS_STEM7_ROWS = 0, 1, 2, 3
+IPC_HANDLE_BYTES = 64
 
 
 class ConvDesc(C.Structure):
@@ -34,7 +35,7 @@ class ConvDesc(C.Structure):
         ("post_add", C.c_void_p),
         ("out", C.c_void_p),
         ("relu", C.c_int), ("out_phase_split", C.c_int), ("out_ld", C.c_int), ("img_mod", C.c_int),
-        ("half_coff", C.c_int), ("max_ctas", C.c_int), ("cluster", C.c_int),
+        ("half_coff", C.c_int), ("max_ctas", C.c_int), ("cluster", C.c_int), ("block_n", C.c_int),
     ]
 
 

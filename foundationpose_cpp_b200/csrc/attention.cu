@@ -22,10 +22,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
-#include <map>
 #include <mutex>
 #include <stdexcept>
-#include <tuple>
 
 #include "net_ops.h"
 #include "ptx.cuh"
@@ -57,13 +55,7 @@ constexpr int kRedBytes = 2 * 2 * kQT * 4;   // row max / row sum exchange
 constexpr int kStageBytes = kQT * kHD * 2;   // output tile staging: 8 warps x (32 rows x 128 B)
 constexpr size_t kSmem = 1024 + 2 * kQBytes + kRing * kChunkBytes + kStageBytes + kRedBytes + 256;
 
-struct Params {
-  CUtensorMap tm_q;   // qkv as (1536, 400, n_hyp), box (64, 128, 1)
-  CUtensorMap tm_kv;  // same tensor, box (64, 80, 1)
-  CUtensorMap tm_out; // out as (out_ld, 400, n_hyp), box (64, 32, 1): one softmax warp's rows x one dim half
-  int n_items;  // n_hyp * heads * query tiles
-  unsigned long long* phase_clocks;  // optional (FPB200_ATTN_PHASES=1): per-phase clock sums of CTA 0
-};
+using Params = AttentionPlan;
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -500,22 +492,27 @@ using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 std::mutex g_mu;
-std::map<std::tuple<const void*, void*, int, int, int>, Params> g_params;
 
 const char* init() {
-  if (g_encode) return nullptr;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess || !fn)
-    return "cuTensorMapEncodeTiled not available from the CUDA driver";
+  // kernel attributes are per device; the driver entry point is process-wide
+  static unsigned long long inited = 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return "cudaGetDevice failed";
+  if (dev < 64 && ((inited >> dev) & 1ull)) return nullptr;
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn)
+      return "cuTensorMapEncodeTiled not available from the CUDA driver";
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
   if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) !=
       cudaSuccess)
     return "cudaFuncSetAttribute(attention smem) failed (not an sm_100a device?)";
-  int dev = 0;
-  cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (dev < 64) inited |= 1ull << dev;
   return nullptr;
 }
 
@@ -563,21 +560,15 @@ bool attention_phase_clocks(unsigned long long out[22]) {
   return cudaMemcpy(out, g_phase_clocks, 22 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess;
 }
 
-void launch_attention(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, cudaStream_t s) {
-  if (n_hyp <= 0) return;
-  if (const char* e = tc::init()) throw std::runtime_error(e);
-  tc::Params prm;
-  {
-    std::lock_guard<std::mutex> lk(tc::g_mu);
-    const auto key = std::make_tuple((const void*)qkv, (void*)out, n_hyp, qkv_ld, out_ld);
-    auto it = tc::g_params.find(key);
-    if (it == tc::g_params.end()) {
-      if (const char* e = tc::make_params(qkv, out, n_hyp, qkv_ld, out_ld, &prm)) throw std::runtime_error(e);
-      tc::g_params[key] = prm;
-    } else {
-      prm = it->second;
-    }
-  }
+const char* build_attention(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, AttentionPlan* plan) {
+  if (n_hyp <= 0) return "attention: no hypotheses";
+  if (const char* e = tc::init()) return e;
+  return tc::make_params(qkv, out, n_hyp, qkv_ld, out_ld, plan);
+}
+
+void launch_attention(const AttentionPlan& plan, cudaStream_t s) {
+  if (plan.n_items <= 0) return;
+  tc::Params prm = plan;
   static const bool want_phases = getenv("FPB200_ATTN_PHASES") != nullptr;
   if (want_phases) {
     if (!g_phase_clocks) cudaMalloc(&g_phase_clocks, 24 * sizeof(unsigned long long));

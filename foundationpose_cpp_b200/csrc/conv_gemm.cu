@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "ptx.cuh"
 
@@ -489,13 +490,23 @@ int g_num_sms = 0;
 }  // namespace
 
 const char* conv_gemm_init() {
-  if (g_encode) return nullptr;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
-    return "cuTensorMapEncodeTiled not available from the CUDA driver";
-  e = cudaSuccess;
+  // The driver entry point is process-wide; kernel attributes are per device (a process may hold sessions on
+  // several GPUs: BASELINE config 5 in one process), so they are set once for every device that gets here.
+  static std::mutex mu;
+  static unsigned long long inited = 0;  // bit d: device d done
+  std::lock_guard<std::mutex> lk(mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return "cudaGetDevice failed";
+  if (dev < 64 && ((inited >> dev) & 1ull)) return nullptr;
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      return "cuTensorMapEncodeTiled not available from the CUDA driver";
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  cudaError_t e = cudaSuccess;
   auto set_attr = [&](auto kernel) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   };
@@ -510,10 +521,9 @@ const char* conv_gemm_init() {
   set_attr(conv_gemm_kernel<256, false, true>);
   set_attr(conv_gemm_kernel<256, true, true>);
   if (e != cudaSuccess) return "cudaFuncSetAttribute(max dynamic smem) failed (not an sm_100a device?)";
-  int dev = 0;
-  cudaGetDevice(&dev);
+  // every B200 has the same SM count; the value is only a tiling heuristic (grid size, tile width)
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (dev < 64) inited |= 1ull << dev;
   return nullptr;
 }
 
@@ -573,7 +583,11 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
         break;
       }
   }
-  if (const char* env = getenv("FPB_GEMM_BN")) {
+  if (d.block_n) {
+    if ((d.block_n != 64 && d.block_n != 128 && d.block_n != 256) || d.cout % d.block_n)
+      return "conv_gemm: block_n must be 64, 128 or 256 and divide cout";
+    bn_tile = d.block_n;
+  } else if (const char* env = getenv("FPB_GEMM_BN")) {
     const int v = atoi(env);
     if ((v == 64 || v == 128 || v == 256) && d.cout % v == 0) bn_tile = v;
   }
@@ -585,7 +599,8 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   const long long m_tiles_all = (long long)((d.out_w + d.bw - 1) / d.bw) * ((d.out_h + d.bh - 1) / d.bh) *
                                 ((d.n_img + d.bn - 1) / d.bn);
   int mode = d.cluster > 0 ? (d.cluster == 1 ? 0 : 2) : (m_tiles_all >= 2 * g_num_sms ? 2 : 0);
-  if (const char* env = getenv("FPB_GEMM_MODE")) mode = atoi(env) ? 2 : 0;
+  if (d.cluster == 0)
+    if (const char* env = getenv("FPB_GEMM_MODE")) mode = atoi(env) ? 2 : 0;
   const int cluster = mode == 0 ? 1 : 2;
   if (d.bn & (d.bn - 1)) return "conv_gemm: bn must be a power of two";
   if ((d.bw * d.bn) % 8) return "conv_gemm: a tile row (bw*bn pixels) must be a whole number of swizzle atoms";

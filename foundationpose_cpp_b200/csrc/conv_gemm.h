@@ -93,6 +93,7 @@ struct ConvGemmDesc {
   int max_ctas = 0;  // 0 -> number of SMs
   int cluster = 0;   // 0 -> automatic; 1 = single CTAs; 2, 3 = CTA pairs issuing
                      // tcgen05.mma.cta_group::2 (M = 256)
+  int block_n = 0;   // 0 -> automatic; 64 / 128 / 256 forces the tile width (tests run every kernel variant)
 };
 
 struct ConvGemmPlan {

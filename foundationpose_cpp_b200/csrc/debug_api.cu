@@ -50,6 +50,7 @@ extern "C" int fpb200_debug_conv_gemm(const fpb200_conv_desc* c, int repeat, flo
     d.half_coff = c->half_coff;
     d.max_ctas = c->max_ctas;
     d.cluster = c->cluster;
+    d.block_n = c->block_n;
     ConvGemmPlan plan;
     if (const char* e = build_conv_gemm(d, &plan)) return fail(FPB200_ERR_INVALID, "%s", e);
     cudaEvent_t e0, e1;
@@ -79,10 +80,12 @@ extern "C" int fpb200_debug_attention(const void* qkv, void* out, int n_hyp, int
     cudaEvent_t e0, e1;
     FPB_CUDA(cudaEventCreate(&e0));
     FPB_CUDA(cudaEventCreate(&e1));
-    launch_attention(q, o, n_hyp, 1536, 512, 0);
+    AttentionPlan ap;
+    if (const char* e = build_attention(q, o, n_hyp, 1536, 512, &ap)) return fail(FPB200_ERR_INVALID, "%s", e);
+    launch_attention(ap, 0);
     FPB_CUDA(cudaGetLastError());
     FPB_CUDA(cudaEventRecord(e0, 0));
-    for (int i = 0; i < repeat; ++i) launch_attention(q, o, n_hyp, 1536, 512, 0);
+    for (int i = 0; i < repeat; ++i) launch_attention(ap, 0);
     FPB_CUDA(cudaEventRecord(e1, 0));
     FPB_CUDA(cudaDeviceSynchronize());
     float ms = 0.f;

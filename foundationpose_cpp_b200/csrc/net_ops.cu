@@ -258,6 +258,7 @@ __global__ void row_dot_kernel(const float* __restrict__ in, const float* __rest
 // (128-d dot product from shared memory, no shuffles); for the weighted sum lane l owns dims
 // [4l, 4l+4).  Row pitch 132 floats keeps the 16-byte shared loads conflict-free.
 constexpr int kCAQ = 8, kCATile = 32, kCAPitch = 132;
+constexpr size_t kCrossAttnMaxSmem = 200 * 1024;
 __global__ void __launch_bounds__(kCAQ * 32)
 cross_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n) {
   extern __shared__ __align__(16) float s_ca[];
@@ -439,6 +440,14 @@ __global__ void refine_update_kernel(const float* __restrict__ mean_t, const flo
 
 }  // namespace
 
+const char* net_ops_init() {
+  // per device (a process may drive several GPUs), idempotent
+  if (cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrossAttnMaxSmem) !=
+      cudaSuccess)
+    return "cudaFuncSetAttribute(cross_attention smem) failed (not an sm_100a device?)";
+  return nullptr;
+}
+
 void launch_layernorm(const __half* x, const float* gamma, const float* beta, __half* out, long long rows,
                       cudaStream_t s) {
   if (rows <= 0) return;
@@ -481,13 +490,7 @@ void launch_cross_attention(const float* qkv, float* out, int n, cudaStream_t s)
   if (n <= 0) return;
   const int n_pad = (n + kCATile - 1) / kCATile * kCATile;
   const size_t smem = sizeof(float) * (kCAQ * 128 + kCATile * kCAPitch + (size_t)kCAQ * n_pad);
-  static size_t smem_set = 48 * 1024;
-  if (smem > smem_set) {
-    if (smem > 200 * 1024) throw std::invalid_argument("cross_attention: too many hypotheses for one shared-memory score row");
-    if (cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      throw std::runtime_error("cudaFuncSetAttribute(cross_attention smem) failed");
-    smem_set = smem;
-  }
+  if (smem > kCrossAttnMaxSmem) throw std::invalid_argument("cross_attention: too many hypotheses for one shared-memory score row");
   dim3 grid((n + kCAQ - 1) / kCAQ, 4);
   cross_attention_kernel<<<grid, kCAQ * 32, smem, s>>>(qkv, out, n);
 }

@@ -2,14 +2,26 @@
 // pose update and ranking.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace fpb {
 
+// Per-device kernel attributes of this file's kernels and of the attention kernel; nullptr on success.
 const char* attention_init();
-// qkv: [n_hyp*400, qkv_ld] fp16 with Q | K | V blocks of 4 heads x 128; out: [n_hyp*400, out_ld].
-void launch_attention(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, cudaStream_t s);
+const char* net_ops_init();
+// Self-attention core.  qkv: [n_hyp*400, qkv_ld] fp16 with Q | K | V blocks of 4 heads x 128; out: [n_hyp*400, out_ld].
+// The plan (three TMA descriptors) belongs to whoever owns the buffers: a network plan, or a debug call.
+struct AttentionPlan {
+  CUtensorMap tm_q;    // qkv as (qkv_ld, 400, n_hyp), box (64, 128, 1)
+  CUtensorMap tm_kv;   // same tensor, box (64, 80, 1)
+  CUtensorMap tm_out;  // out as (out_ld, 400, n_hyp), box (64, 32, 1): one softmax warp's rows x one dim half
+  int n_items = 0;     // n_hyp * heads * query tiles
+  unsigned long long* phase_clocks = nullptr;  // optional (FPB200_ATTN_PHASES=1): per-phase clock sums of CTA 0
+};
+const char* build_attention(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, AttentionPlan* plan);
+void launch_attention(const AttentionPlan& plan, cudaStream_t s);
 bool attention_phase_clocks(unsigned long long out[22]);
 
 // out = LayerNorm(x) * gamma + beta over 512 channels, eps 1e-5 (post-LN of nn.TransformerEncoderLayer;

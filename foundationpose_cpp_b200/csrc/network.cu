@@ -115,6 +115,7 @@ Network::Network(NetKind kind, const std::string& weight_path, Arena* arena)
     : kind_(kind), w_(new WeightFile(weight_path, (int)kind)), arena_(arena) {
   if (const char* e = conv_gemm_init()) throw std::runtime_error(e);
   if (const char* e = attention_init()) throw std::runtime_error(e);
+  if (const char* e = net_ops_init()) throw std::runtime_error(e);
   flops_per_hyp_ = plan(1).flops;
 }
 
@@ -133,6 +134,11 @@ void add_gemm(std::vector<std::function<void(cudaStream_t)>>& steps, double* flo
     g_gemm_flops_sink->resize(steps.size(), 0.0);
     (*g_gemm_flops_sink)[steps.size() - 1] = pl.flops;
   }
+}
+void add_attention(std::vector<std::function<void(cudaStream_t)>>& steps, const __half* qkv, __half* out, int n) {
+  AttentionPlan ap;
+  if (const char* e = build_attention(qkv, out, n, 1536, 512, &ap)) throw std::runtime_error(e);
+  steps.push_back([ap](cudaStream_t s) { launch_attention(ap, s); });
 }
 }  // namespace
 
@@ -207,7 +213,7 @@ void Network::add_encoder_layer(Plan& p, int n, const std::string& h, float* mea
   const WeightFile& W = *w_;
   const long long rows = (long long)n * 400;
   add_gemm(p.steps, &p.flops, linear_desc(A.d0, rows, 512, W.f16(h + ".qkv.w", 1536, 512), W.f32(h + ".qkv.b", 1536), 1536, A.qkv, false));
-  p.steps.push_back([&A, n](cudaStream_t s) { launch_attention(A.qkv, A.att, n, 1536, 512, s); });
+  add_attention(p.steps, A.qkv, A.att, n);
   p.flops += 2.0 * n * 4 * 2 * 400.0 * 400.0 * 128.0;
   // post-LN encoder layer: the two residual sums are formed in the GEMM epilogues
   add_gemm(p.steps, &p.flops, linear_desc(A.att, rows, 512, W.f16(h + ".out.w", 512, 512), W.f32(h + ".out.b", 512), 512, A.proj, false, A.d0));
@@ -236,7 +242,7 @@ Network::Plan& Network::plan(int n) {
     const WeightFile& W = *w_;
     const long long rows = (long long)n * 400;
     add_gemm(p->steps, &p->flops, linear_desc(A.d0, rows, 512, W.f16("att.qkv.w", 1536, 512), W.f32("att.qkv.b", 1536), 1536, A.qkv, false));
-    p->steps.push_back([&A, n](cudaStream_t s) { launch_attention(A.qkv, A.att, n, 1536, 512, s); });
+    add_attention(p->steps, A.qkv, A.att, n);
     p->flops += 2.0 * n * 4 * 2 * 400.0 * 400.0 * 128.0;
     p->steps.push_back([&A, n](cudaStream_t s) { launch_token_mean(A.att, A.mean_t, n, s); });
     // out_proj is applied to the token mean by the session (it commutes with the mean)

@@ -831,19 +831,14 @@ void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float dia
 
 int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr, __half* packed,
                   int img0, int32_t* rast_id_debug, int* status, unsigned long long* zbuf_scratch, int zbuf_poses,
-                  cudaStream_t s) {
+                  int num_sms, int split_mode, cudaStream_t s) {
   if (n <= 0) return 0;
   vertex_stage_kernel<<<dim3((mesh.num_vertices + 255) / 256, n), 256, 0, s>>>(mesh, aux, vclip, vattr);
-  static const int sms = [] {
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
-  // band kernel: 4 CTAs per hypothesis and 4 resident CTAs per SM; below ~2 CTAs per SM it is bound by the
+  const int sms = num_sms > 0 ? num_sms : 148;
+  // band kernel: 2 CTAs per hypothesis and 2 resident CTAs per SM; below ~2 CTAs per SM it is bound by the
   // latency of one CTA walking every triangle (N = 1 and N = 32 take the same ~105 us)
   bool split = n * 4 <= 2 * sms;
-  if (const char* e = getenv("FPB200_RENDER_SPLIT")) split = e[0] != '0';  // tests run both paths on the same input
+  if (split_mode >= 0) split = split_mode != 0;  // tests run both paths on the same input
   if (split && zbuf_scratch && n <= zbuf_poses) {
     // few hypotheses: spread the triangles over the machine (see raster_split_kernel)
     cudaMemsetAsync(zbuf_scratch, 0xFF, sizeof(unsigned long long) * (size_t)n * kCrop * kCrop, s);

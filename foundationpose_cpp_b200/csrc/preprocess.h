@@ -67,10 +67,12 @@ void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float dia
 // zbuf_poses * 160 * 160 keys; with n <= zbuf_poses and few enough hypotheses to leave SMs idle the
 // triangles are spread over the whole machine on global z-buffers (identical result).
 constexpr int kSplitRenderPoses = 80;
-// Returns the number of kernels launched.
+// rast_id_debug (may be null: the product path passes null unless a test asked for the ids) receives the
+// visibility id map [n,160,160] (triangle + 1, 0 = empty; GL row order).  num_sms: SM count of the session's
+// device; split_mode: -1 automatic, 0 band kernel, 1 split kernels.  Returns the number of kernels launched.
 int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr,
                    __half* packed, int img0, int32_t* rast_id_debug, int* status,
-                   unsigned long long* zbuf_scratch, int zbuf_poses, cudaStream_t s);
+                   unsigned long long* zbuf_scratch, int zbuf_poses, int num_sms, int split_mode, cudaStream_t s);
 // Crop/warp the observed rgb + xyz, normalise, pack into packed image `img0 + i`.
 void launch_warp(const uint8_t* rgb, const float* xyz, int h, int w, const PoseAux* aux, int n,
                  float diameter, __half* packed, int img0, cudaStream_t s);

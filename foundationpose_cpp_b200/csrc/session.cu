@@ -156,6 +156,91 @@ struct HostResult {
   int status;
 };
 
+// ---- multi-GPU exchange over peer memory -------------------------------------------------------------
+// The path has exactly one exchange: the scorer's cross-hypothesis attention needs every
+// hypothesis's 512-d feature, and the winner's refined pose must be known everywhere.  One process per GPU;
+// each rank owns a REGION in its own HBM that its peers map through CUDA IPC (NVLink / NVSwitch peer
+// access).  A Register then contains no library collective at all: the rank's rows are stored straight into
+// every peer's region by exchange_push_kernel, followed by a release-store of the call's epoch into the peer's
+// arrival flag; exchange_collect_kernel acquires all flags and compacts the rows for the tail.  Everything is
+// kernels on the session stream, so the whole sharded Register is one CUDA-graph replay.
+// Region layout (floats): rows [2][cap_total][kExchLd] | flags u32[kMaxWorld] | epoch u32.
+// Rows are double-buffered by epoch parity: a peer can only be one exchange ahead (it needs this rank's flag of
+// epoch e + 1 before it finishes e + 1), so its stores of e + 1 never touch the buffer this rank still reads for e.
+constexpr int kMaxWorld = 16;
+constexpr int kExchTailWords = kMaxWorld + 16;  // flags + epoch (+ padding)
+struct ExchPeers {
+  float* rows[kMaxWorld];     // region base of every rank (own region included)
+  unsigned* flags[kMaxWorld]; // arrival flags of every rank's region
+  unsigned* epoch;            // this rank's exchange counter (device memory: graph replays cannot change arguments)
+  int world, rank, cap_total;
+};
+constexpr int kStatusExchangeTimeout = 8;
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void exchange_begin_kernel(unsigned* epoch) { *epoch += 1; }
+
+// grid = world (one CTA per destination rank): local rows [lo, lo + nl) = 512 feature floats + 16 pose floats.
+__global__ void __launch_bounds__(1024)
+exchange_push_kernel(ExchPeers P, const float* __restrict__ feats, const float* __restrict__ poses, int lo, int nl) {
+  const int peer = blockIdx.x;
+  const unsigned e = *P.epoch;
+  float4* dst = reinterpret_cast<float4*>(P.rows[peer] + ((size_t)(e & 1u) * P.cap_total + lo) * kExchLd);
+  constexpr int kRow4 = kExchLd / 4;  // 132 float4 per row: 128 feature + 4 pose
+  const float4* f4 = reinterpret_cast<const float4*>(feats);
+  const float4* p4 = reinterpret_cast<const float4*>(poses);
+  for (int i = threadIdx.x; i < nl * kRow4; i += blockDim.x) {
+    const int r = i / kRow4, c = i - r * kRow4;
+    dst[i] = c < 128 ? f4[r * 128 + c] : p4[r * 4 + (c - 128)];
+  }
+  __threadfence_system();  // every thread's stores are visible system-wide before the flag is
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys(P.flags[peer] + P.rank, e);
+}
+
+// Waits until every rank's rows of this epoch have arrived in the local region, then compacts them into the
+// dense [n,512] feature and [n,16] pose arrays the tail reads.  A rank that never arrives (a peer that skipped
+// the call, or died) raises kStatusExchangeTimeout after ~2 s instead of hanging the GPU.
+__global__ void __launch_bounds__(256)
+exchange_collect_kernel(ExchPeers P, float* __restrict__ feats, float* __restrict__ poses, int n, int* status) {
+  const unsigned e = *P.epoch;
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < P.world) {
+    const unsigned* flag = P.flags[P.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - e) < 0) {
+      if (clock64() - t0 > 4000000000LL) {
+        timed_out = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (timed_out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(status, kStatusExchangeTimeout);
+    return;
+  }
+  const float4* src = reinterpret_cast<const float4*>(P.rows[P.rank] + (size_t)(e & 1u) * P.cap_total * kExchLd);
+  constexpr int kRow4 = kExchLd / 4;
+  float4* f4 = reinterpret_cast<float4*>(feats);
+  float4* p4 = reinterpret_cast<float4*>(poses);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * kRow4; i += gridDim.x * blockDim.x) {
+    const int r = i / kRow4, c = i - r * kRow4;
+    const float4 v = __ldcg(src + i);  // peers wrote these through NVLink: read at L2, never a stale L1 line
+    if (c < 128) f4[r * 128 + c] = v; else p4[r * 4 + (c - 128)] = v;
+  }
+}
+
 }  // namespace
 
 struct fpb200_session {
@@ -199,9 +284,27 @@ struct fpb200_session {
   bool async_stages = false;  // stage calls return without synchronising the stream
   bool mask_resident = false;
   bool profile_gemm = false;
+  int num_sms = 148;
+  // test switches (fpb200_debug_options): visibility ids are only written when a test asked for them
+  // (25.8 MB per render at N = 252 that nothing on the product path reads)
+  bool debug_ids = false;
+  int render_split = -1;  // -1 automatic, 0 band kernel, 1 split kernels
+  bool pending_async = false;  // an async call's pinned staging / result has not been collected yet
+  // Multi-GPU exchange over NVLink peer memory (fpb200_exchange_*): every rank owns one region
+  // [2 epochs][max_hyps][528] f32 + arrival flags; ranks store their rows straight into every peer's region.
+  DevBuf<float> exch_region;
+  ExchPeers peers{};
+  std::vector<void*> ipc_opened;
+  bool exchange_ready = false;
+
+  void drop_graphs() {
+    for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    graphs.clear();
+  }
 
   ~fpb200_session() {
-    for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    drop_graphs();
+    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
     if (host_result) cudaFreeHost(host_result);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -297,8 +400,9 @@ void do_render_and_transform(fpb200_session* s, float crop_ratio) {
   const int nl = s->hi - s->lo;
   const MeshEntry& m = *s->cur_mesh;
   launch_pose_setup(s->poses.p + 16 * s->lo, nl, s->intr, m.dm.diameter, crop_ratio, s->aux.p, s->stream);
-  const int k_render = launch_render(m.dm, s->aux.p, nl, s->vclip.p, s->vattr.p, s->arena->packed, 0, s->rast_id.p,
-                                     s->status.p, s->zbuf.p, kSplitRenderPoses, s->stream);
+  const int k_render = launch_render(m.dm, s->aux.p, nl, s->vclip.p, s->vattr.p, s->arena->packed, 0,
+                                     s->debug_ids ? s->rast_id.p : nullptr, s->status.p, s->zbuf.p, kSplitRenderPoses,
+                                     s->num_sms, s->render_split, s->stream);
   launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->stream);
   s->count_launches(2 + k_render);
   s->crop_ratio_last = crop_ratio;
@@ -352,12 +456,21 @@ void do_score_features(fpb200_session* s) {
   launch_small_linear(s->arena->mean_t, W.f32("att.out.w", 512, 512), W.f32("att.out.b", 512), s->feats.p, nl, 512,
                       512, s->stream);
   // The exchange rows only exist to cross GPUs; a single-GPU session ranks straight from feats / poses.
-  if (s->opt.shard_world > 1) {
+  int extra = 0;
+  if (s->exchange_ready) {
+    // peer-memory exchange: this rank's rows go straight into every rank's region (NVLink stores)
+    exchange_begin_kernel<<<1, 1, 0, s->stream>>>(s->peers.epoch);
+    exchange_push_kernel<<<s->peers.world, 1024, 0, s->stream>>>(s->peers, s->feats.p, s->poses.p + 16 * s->lo, s->lo, nl);
+    FPB_CUDA(cudaGetLastError());
+    extra = 2;
+  } else if (s->opt.shard_world > 1) {
+    // host-driven exchange: the caller all-gathers the packed rows (fpb200_feature_buffers)
     pack_exchange_kernel<<<(nl * kExchLd + 255) / 256, 256, 0, s->stream>>>(s->feats.p, s->poses.p + 16 * s->lo,
                                                                            s->exch_local.p, nl);
     FPB_CUDA(cudaGetLastError());
+    extra = 1;
   }
-  s->count_launches(s->scorer->launches_per_forward(nl) + (s->opt.shard_world > 1 ? 2 : 1));
+  s->count_launches(s->scorer->launches_per_forward(nl) + 1 + extra);
   s->features_ready = true;
 }
 
@@ -366,7 +479,11 @@ void do_score_finish(fpb200_session* s) {
   const int n = s->n_hyp;
   const WeightFile& W = s->scorer->weights();
   const float* all_poses = s->poses.p;
-  if (s->opt.shard_world > 1) {
+  if (s->exchange_ready) {
+    exchange_collect_kernel<<<16, 256, 0, s->stream>>>(s->peers, s->feats.p, s->all_poses.p, n, s->status.p);
+    FPB_CUDA(cudaGetLastError());
+    all_poses = s->all_poses.p;
+  } else if (s->opt.shard_world > 1) {
     unpack_exchange_kernel<<<(n * kExchLd + 255) / 256, 256, 0, s->stream>>>(s->exch_all.p, s->feats.p, s->all_poses.p,
                                                                             n, s->opt.shard_world, s->shard_cap);
     FPB_CUDA(cudaGetLastError());
@@ -391,9 +508,12 @@ void enqueue_result_read(fpb200_session* s) {
 
 int wait_result(fpb200_session* s, float out_pose[16], int* best_index) {
   FPB_CUDA(cudaStreamSynchronize(s->stream));
+  s->pending_async = false;
   const int st = s->host_result->status;
   if (st & kStatusEmptyMask) return fail(FPB200_ERR_NO_DEPTH, "[FoundationposeSampling] Mask is all zero.");
   if (st & kStatusNoDepth) return fail(FPB200_ERR_NO_DEPTH, "[FoundationposeSampling] No valid value in mask.");
+  if (st & kStatusExchangeTimeout)
+    return fail(FPB200_ERR_STATE, "multi-GPU exchange timed out: a peer rank did not take part in this call");
   if (out_pose) memcpy(out_pose, s->host_result->pose, sizeof(float) * 16);
   if (best_index) *best_index = s->host_result->best_index;
   return FPB200_OK;
@@ -548,8 +668,14 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
     s->grid.upload(grid.data(), grid.size());
     s->poses.alloc((size_t)cap * 16); s->all_poses.alloc((size_t)cap * 16);
     s->center.alloc(4); s->status.alloc(1); s->best_index.alloc(1); s->best_pose.alloc(16);
-    s->aux.alloc(cap); s->rast_id.alloc((size_t)cap * kCrop * kCrop);
+    s->aux.alloc(cap);  // rast_id: allocated by fpb200_debug_options when a test asks for the ids
+    FPB_CUDA(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, s->opt.device));
     s->zbuf.alloc((size_t)std::min(cap, kSplitRenderPoses) * kCrop * kCrop);
+    if (s->opt.shard_world > 1) {
+      FPB_REQUIRE(s->opt.shard_world <= kMaxWorld, "shard_world > %d is not supported", kMaxWorld);
+      s->exch_region.alloc((size_t)2 * cap * kExchLd + kExchTailWords);
+      FPB_CUDA(cudaMemset(s->exch_region.p, 0, sizeof(float) * s->exch_region.n));
+    }
     s->exch_local.alloc((size_t)cap * kExchLd);
     s->exch_all.alloc(((size_t)cap + s->opt.shard_world) * kExchLd);
     s->feats.alloc((size_t)cap * 512); s->tail_qkv.alloc((size_t)cap * 1536); s->tail_att.alloc((size_t)cap * 512);
@@ -586,7 +712,9 @@ int fpb200_register(fpb200_session* s, const uint8_t* rgb, const float* depth, c
                     const char* target_name, int refine_itr, float out_pose[16]) {
   return guard([&]() -> int {
     FPB_REQUIRE(s && out_pose, "null session / output");
-    FPB_REQUIRE(s->opt.shard_world == 1, "fpb200_register needs shard_world == 1; sharded sessions use the stage API");
+    FPB_REQUIRE(s->opt.shard_world == 1 || s->exchange_ready,
+                "a sharded session needs fpb200_exchange_connect before fpb200_register (or the stage API with a "
+                "host-driven all-gather)");
     MeshEntry* mesh = s->find_mesh(target_name);
     FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
     FPB_REQUIRE(refine_itr >= 0, "refine_itr must be >= 0");
@@ -617,7 +745,8 @@ int fpb200_register(fpb200_session* s, const uint8_t* rgb, const float* depth, c
 int fpb200_register_async(fpb200_session* s, const char* target_name, int refine_itr) {
   return guard([&]() -> int {
     FPB_REQUIRE(s, "null session");
-    FPB_REQUIRE(s->opt.shard_world == 1, "fpb200_register_async needs shard_world == 1; sharded sessions use the stage API");
+    FPB_REQUIRE(s->opt.shard_world == 1 || s->exchange_ready,
+                "a sharded session needs fpb200_exchange_connect before fpb200_register_async");
     if (!s->uploaded) return fail(FPB200_ERR_STATE, "fpb200_upload must be called first");
     MeshEntry* mesh = s->find_mesh(target_name);
     FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
@@ -647,6 +776,10 @@ int fpb200_track_async(fpb200_session* s, const uint8_t* rgb, const float* depth
     MeshEntry* mesh = s->find_mesh(target_name);
     FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
     FPB_REQUIRE(refine_itr >= 0, "refine_itr must be >= 0");
+    // one call in flight per session: the pinned staging (hypothesis in, pose out) is single-buffered, so a
+    // second async call first lets the previous one finish (its result stays readable until then)
+    if (s->pending_async) FPB_CUDA(cudaStreamSynchronize(s->stream));
+    s->pending_async = true;
     reset_call(s);
     do_upload(s, rgb, depth, h, w);
     memcpy(s->host_result->hyp, hyp_pose, sizeof(float) * 16);  // pinned staging: the caller's array may go away
@@ -670,6 +803,7 @@ int fpb200_track_wait(fpb200_session* s, float out_pose[16]) {
   return guard([&]() -> int {
     FPB_REQUIRE(s && out_pose, "null session / output");
     FPB_CUDA(cudaStreamSynchronize(s->stream));
+    s->pending_async = false;
     memcpy(out_pose, s->host_result->pose, sizeof(float) * 16);
     return FPB200_OK;
   });
@@ -803,7 +937,24 @@ int fpb200_read_buffer(fpb200_session* s, const char* name, void* host_dst, size
     else if (nm == "trans") { src = s->trans.p; bytes = sizeof(float) * 3 * nl; }
     else if (nm == "rot") { src = s->rot.p; bytes = sizeof(float) * 3 * nl; }
     else if (nm == "features") { src = s->feats.p; bytes = sizeof(float) * 512 * s->n_hyp; }
-    else if (nm == "rast_id") { src = s->rast_id.p; bytes = sizeof(int32_t) * kCrop * kCrop * nl; }
+    else if (nm == "rast_id") {
+      FPB_REQUIRE(s->debug_ids && s->rast_id.p, "rast_id is only written after fpb200_debug_options(s, 1, ...)");
+      src = s->rast_id.p; bytes = sizeof(int32_t) * kCrop * kCrop * nl;
+    }
+    else if (nm == "crop_tf" || nm == "bbox2d") {
+      // per-hypothesis crop transform (row-major 3x3) / bbox2d (l, t, r, b) of the LAST render_and_transform
+      const bool tf = nm == "crop_tf";
+      bytes = sizeof(float) * (tf ? 9 : 4) * nl;
+      FPB_REQUIRE(capacity >= bytes, "buffer '%s' needs %zu bytes, got %zu", name, bytes, capacity);
+      FPB_CUDA(cudaStreamSynchronize(s->stream));
+      std::vector<PoseAux> aux(nl);
+      FPB_CUDA(cudaMemcpy(aux.data(), s->aux.p, sizeof(PoseAux) * nl, cudaMemcpyDeviceToHost));
+      float* dst = static_cast<float*>(host_dst);
+      for (int i = 0; i < nl; ++i)
+        memcpy(dst + (size_t)i * (tf ? 9 : 4), tf ? aux[i].tf : aux[i].bbox, sizeof(float) * (tf ? 9 : 4));
+      if (written) *written = bytes;
+      return FPB200_OK;
+    }
     else if (nm == "tokens") { src = s->arena->d0; bytes = (size_t)2 * 400 * 512 * nl; }
     else if (nm == "center") { src = s->center.p; bytes = sizeof(float) * 3; }
     else if (nm == "status") { src = s->status.p; bytes = sizeof(int); }
@@ -873,6 +1024,107 @@ int fpb200_wait(fpb200_session* s, int* best_index, float out_pose[16]) {
   return guard([&]() -> int {
     FPB_REQUIRE(s, "null session");
     return wait_result(s, out_pose, best_index);
+  });
+}
+
+namespace {
+// Wires the session's view of all regions: base[r] = device pointer to rank r's region (mapped or local).
+void wire_exchange(fpb200_session* s, void* const* base) {
+  const int world = s->opt.shard_world, cap = s->opt.max_hyps;
+  ExchPeers& P = s->peers;
+  memset(&P, 0, sizeof(P));
+  for (int r = 0; r < world; ++r) {
+    P.rows[r] = static_cast<float*>(base[r]);
+    P.flags[r] = reinterpret_cast<unsigned*>(P.rows[r] + (size_t)2 * cap * kExchLd);
+  }
+  P.epoch = P.flags[s->opt.shard_rank] + kMaxWorld;
+  P.world = world;
+  P.rank = s->opt.shard_rank;
+  P.cap_total = cap;
+  s->exchange_ready = true;
+  s->drop_graphs();
+}
+}  // namespace
+
+int fpb200_exchange_export(fpb200_session* s, unsigned char handle[FPB200_IPC_HANDLE_BYTES]) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && handle, "null argument");
+    FPB_REQUIRE(s->opt.shard_world > 1 && s->exch_region.p, "fpb200_exchange_export needs a session with shard_world > 1");
+    static_assert(sizeof(cudaIpcMemHandle_t) == FPB200_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    FPB_CUDA(cudaIpcGetMemHandle(&h, s->exch_region.p));
+    memcpy(handle, &h, sizeof(h));
+    return FPB200_OK;
+  });
+}
+
+int fpb200_exchange_connect(fpb200_session* s, const unsigned char* handles) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && handles, "null argument");
+    FPB_REQUIRE(s->opt.shard_world > 1 && s->exch_region.p, "fpb200_exchange_connect needs a session with shard_world > 1");
+    FPB_REQUIRE(!s->exchange_ready, "the exchange is already connected");
+    FPB_CUDA(cudaSetDevice(s->opt.device));
+    void* base[kMaxWorld] = {};
+    for (int r = 0; r < s->opt.shard_world; ++r) {
+      if (r == s->opt.shard_rank) {
+        base[r] = s->exch_region.p;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + (size_t)r * FPB200_IPC_HANDLE_BYTES, sizeof(h));
+      void* ptr = nullptr;
+      FPB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      s->ipc_opened.push_back(ptr);
+      base[r] = ptr;
+    }
+    wire_exchange(s, base);
+    return FPB200_OK;
+  });
+}
+
+int fpb200_exchange_connect_local(fpb200_session* const* sessions, int world) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(sessions && world > 1 && world <= kMaxWorld, "bad session list");
+    void* base[kMaxWorld] = {};
+    for (int r = 0; r < world; ++r) {
+      fpb200_session* s = sessions[r];
+      FPB_REQUIRE(s && s->opt.shard_world == world && s->opt.shard_rank == r && s->exch_region.p,
+                  "session %d is not rank %d of %d", r, r, world);
+      FPB_REQUIRE(s->opt.max_hyps == sessions[0]->opt.max_hyps, "all ranks must have the same capacity");
+      base[r] = s->exch_region.p;
+    }
+    for (int r = 0; r < world; ++r) {
+      fpb200_session* s = sessions[r];
+      FPB_CUDA(cudaSetDevice(s->opt.device));
+      for (int q = 0; q < world; ++q) {
+        const int dq = sessions[q]->opt.device;
+        if (dq == s->opt.device) continue;
+        int can = 0;
+        FPB_CUDA(cudaDeviceCanAccessPeer(&can, s->opt.device, dq));
+        FPB_REQUIRE(can, "device %d cannot access device %d", s->opt.device, dq);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(dq, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FPB_CUDA(e);
+        (void)cudaGetLastError();
+      }
+      wire_exchange(s, base);
+    }
+    return FPB200_OK;
+  });
+}
+
+int fpb200_debug_options(fpb200_session* s, int write_rast_ids, int render_split) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s, "null session");
+    FPB_REQUIRE(render_split >= -1 && render_split <= 1, "render_split must be -1 (automatic), 0 or 1");
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    if (write_rast_ids && !s->rast_id.p) {
+      const int local_cap = (s->opt.max_hyps + s->opt.shard_world - 1) / s->opt.shard_world;
+      s->rast_id.alloc((size_t)local_cap * kCrop * kCrop);
+    }
+    s->debug_ids = write_rast_ids != 0;
+    s->render_split = render_split;
+    s->drop_graphs();  // captured launch sequences carry the old pointers / kernel choice
+    return FPB200_OK;
   });
 }
 

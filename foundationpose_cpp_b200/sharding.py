@@ -32,3 +32,17 @@ def padded_row(n: int, world: int, row: int) -> int:
         rank = rem + (row - rem * (base + 1)) // max(base, 1)
         start = rem * (base + 1) + (rank - rem) * base
     return rank * shard_capacity(n, world) + (row - start)
+
+
+def gather_handles(handle: bytes, dist=None, device=None):
+    """All ranks' exchange handles in rank order (the list fpb200_exchange_connect wants).  `dist` is an
+    initialised torch.distributed (gloo or nccl); the 64 bytes travel as a uint8 tensor, on `device` for nccl."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    world = dist.get_world_size()
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+    out = torch.empty(world * len(handle), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, mine)
+    flat = bytes(out.cpu().tolist())
+    return [flat[i * len(handle):(i + 1) * len(handle)] for i in range(world)]

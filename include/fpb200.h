@@ -119,12 +119,35 @@ int fpb200_feature_buffers(fpb200_session* s, void** local_dev, int* n_local, in
  * (fp/src/foundationpose.cpp:432-446, fp/src/foundationpose_decoder.cu:24-35). */
 int fpb200_score_finish(fpb200_session* s, int* best_index, float out_pose[16]);
 
+/* ---- multi-GPU: the N hypotheses of ONE Register sharded over the GPUs of a node, one process per GPU ----
+ * The reference has no multi-GPU path; this is the exchange SURVEY.md section 8(e) derives from the scorer's
+ * cross-hypothesis attention: every rank needs all [N,512] features (+ the refined poses, for the winner).
+ * It runs over NVLink peer memory inside the library: each session (shard_world > 1) owns an exchange region
+ * in its HBM; fpb200_exchange_export yields its CUDA IPC handle, the host program hands every rank the handles
+ * of all ranks (any transport: torch.distributed, MPI, a file), fpb200_exchange_connect maps them.  After that
+ * fpb200_register / fpb200_register_async work on sharded sessions: each rank renders / refines / scores its
+ * shard, stores its rows straight into every peer's region and ranks all N redundantly, so every rank returns
+ * the same pose.  All ranks must make the same sequence of Register calls (a missing peer is reported as
+ * FPB200_ERR_STATE after ~2 s, never a hang).  fpb200_exchange_connect_local does the same for sessions that
+ * live in ONE process (tests; several GPUs driven by one host thread). */
+#define FPB200_IPC_HANDLE_BYTES 64
+int fpb200_exchange_export(fpb200_session* s, unsigned char handle[FPB200_IPC_HANDLE_BYTES]);
+int fpb200_exchange_connect(fpb200_session* s, const unsigned char* handles /* [shard_world][64], rank order */);
+int fpb200_exchange_connect_local(fpb200_session* const* sessions, int world);
+
 /* Copy a named device buffer of the session to the host (tests): "render_input" / "transf_input"
  * (f16 [n,160,160,8] packed rgb+xyz+2 pad), "xyz_map" (f32 [h,w,3]), "scores" (f32 [n]),
- * "trans" / "rot" (f32 [n,3]), "features" (f32 [n,512]), "rast_id" (i32 [n,160,160]),
- * "crop_tf" (f32 [n,9] row-major), "bbox2d" (f32 [n,4]), "depth_filtered" (f32 [h,w]). */
+ * "trans" / "rot" (f32 [n,3]), "features" (f32 [n,512]), "rast_id" (i32 [n,160,160]; needs
+ * fpb200_debug_options(s, 1, ...)), "crop_tf" (f32 [n,9] row-major) / "bbox2d" (f32 [n,4]) of the last
+ * render_and_transform, "depth_filtered" (f32 [h,w]), "tokens" (f16 [n,400,512]), "center" (f32 [3]),
+ * "status" (i32), "pose_aux" (raw per-hypothesis constants). */
 int fpb200_read_buffer(fpb200_session* s, const char* name, void* host_dst, size_t capacity_bytes,
                        size_t* bytes_written);
+/* Test switches.  write_rast_ids != 0: every render also writes the visibility id map read back as "rast_id"
+ * (off by default: nothing on the product path reads it).  render_split: -1 automatic, 0 = one CTA per
+ * (band, hypothesis) on shared-memory z-buffers, 1 = triangles spread over all SMs on global z-buffers
+ * (what few-hypothesis launches use); both give identical ids.  Drops captured CUDA graphs. */
+int fpb200_debug_options(fpb200_session* s, int write_rast_ids, int render_split);
 /* Device-side duration of the stages of the last Register/Track (CUDA events), in ms:
  * [0] upload+xyz [1] sampler [2] unused [3] refine iterations (render, warp, net, pose update)
  * [4] score preprocess + scorer net [5] scorer tail + argmax [6] unused; returns the number filled. */
@@ -184,7 +207,8 @@ typedef struct {
   const float* post_add;
   void* out; /* f16 */
   int relu, out_phase_split, out_ld, img_mod, half_coff, max_ctas;
-  int cluster; /* 0 = automatic, 1 = single CTAs, 2 = CTA pairs + weight multicast, 3 = CTA pairs + cta_group::2 MMA */
+  int cluster; /* 0 = automatic, 1 = single CTAs, 2 or 3 = CTA pairs issuing tcgen05.mma.cta_group::2 (M = 256) */
+  int block_n; /* 0 = automatic, 64 / 128 / 256 = forced tile width (parity tests run every kernel variant) */
 } fpb200_conv_desc;
 /* Runs the tcgen05 implicit-GEMM kernel once (+ `repeat` timed launches; avg ms -> *ms_out). */
 int fpb200_debug_conv_gemm(const fpb200_conv_desc* desc, int repeat, float* ms_out);

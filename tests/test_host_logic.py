@@ -123,6 +123,9 @@ allbuf = torch.empty(world * cap, sharding.EXCH_LD)
 dist.all_gather_into_tensor(allbuf, local)
 dense = torch.stack([allbuf[sharding.padded_row(n, world, i)] for i in range(n)])
 assert torch.equal(dense[:, 0], torch.arange(n, dtype=torch.float32)), dense[:, 0]
+# exchange-handle plumbing of the peer-memory exchange (fpb200_exchange_export -> gather -> fpb200_exchange_connect)
+handles = sharding.gather_handles(bytes([rank + 1] * 64), dist)
+assert handles == [bytes([r + 1] * 64) for r in range(world)], handles
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)

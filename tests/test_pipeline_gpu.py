@@ -81,13 +81,13 @@ def _fp16_close(got, ref, what):
     assert frac <= 1e-3, f"{what}: {frac:.2e} of elements differ from the fp16-rounded oracle"
 
 
-@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("split", [0, 1])
 @pytest.mark.parametrize("crop_ratio", [1.2, 1.1])
-def test_render_and_transform_parity(env, crop_ratio, split, monkeypatch):
+def test_render_and_transform_parity(env, crop_ratio, split):
     # split = "1": the few-hypotheses path (triangles spread over all SMs on global z-buffers, then a shading
     # kernel: what Track uses); "0": one CTA per (band, hypothesis) on a shared-memory z-buffer (Register)
-    monkeypatch.setenv("FPB200_RENDER_SPLIT", split)
     m = env["model"]
+    m.debug_options(rast_ids=True, render_split=split)
     m.upload(env["rgb"], env["depth"])
     poses = O.sample_hypotheses(env["depth"], env["mask"], env["K"])[[0, 7, 50, 101, 200, 251]]
     poses = np.concatenate([poses, env["gt"][None]], 0)
@@ -104,6 +104,11 @@ def test_render_and_transform_parity(env, crop_ratio, split, monkeypatch):
     _fp16_close(m.read_packed("render_input", n), ren, "render_input")
     status = m.read_buffer("status", np.int32, 1)[0]
     assert status == 0
+    # the crop transform / bbox2d the C ABI serves == ComputeCropWindowTF / ConstructBBox2D of the oracle
+    np.testing.assert_array_equal(m.read_buffer("crop_tf", np.float32, n * 9).reshape(n, 3, 3), info["tf"].astype(F))
+    np.testing.assert_array_equal(m.read_buffer("bbox2d", np.float32, n * 4).reshape(n, 4),
+                                  O.bbox2d_from_tf(info["tf"]).astype(F))
+    m.debug_options()  # back to the product defaults (no id writes, automatic render path)
 
 
 def _net_close(got, ref, what):

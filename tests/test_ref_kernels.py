@@ -67,6 +67,7 @@ def test_product_raster_matches_reference_cudaraster(tmp_path):
     rgb, depth, mask, gt = synth.make_scene(mesh)
     rp, sp = helpers.write_seeded_weights(str(tmp_path))
     model = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], synth.DEFAULT_K, 480, 640)
+    model.debug_options(rast_ids=True)
     model.upload(rgb, depth)
     poses = np.concatenate([gt[None], O.sample_hypotheses(depth, mask, synth.DEFAULT_K)[::23]], 0)
     n = len(poses)
@@ -113,13 +114,10 @@ def test_polygon_clipper_matches_reference_cudaraster(tmp_path):
     rp, sp = helpers.write_seeded_weights(str(tmp_path))
     model = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], synth.DEFAULT_K, 480, 640)
     model.upload(rgb, depth)
-    for split in ("0", "1"):
-        os.environ["FPB200_RENDER_SPLIT"] = split
-        try:
-            model.set_hypotheses(g["poses_near"], "g")
-            model.render_and_transform(1.2)
-        finally:
-            del os.environ["FPB200_RENDER_SPLIT"]
+    for split in (0, 1):
+        model.debug_options(rast_ids=True, render_split=split)
+        model.set_hypotheses(g["poses_near"], "g")
+        model.render_and_transform(1.2)
         got = model.read_buffer("rast_id", np.int32, n * 160 * 160).reshape(n, 160, 160)
         d = int((got != ref).sum())
         assert d == 0, f"product (split={split}): {d} visibility ids differ from cudaraster"

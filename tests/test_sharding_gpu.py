@@ -83,3 +83,34 @@ def test_sharded_register_equals_single_session(setup, world):
         assert idx == int(np.argmax(setup["scores"]))
         assert np.array_equal(scores, setup["scores"]), float(np.abs(scores - setup["scores"]).max())
         assert np.array_equal(pose, setup["pose"])
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_peer_memory_exchange_register_equals_single_session(setup, world):
+    """The in-library exchange (fpb200_exchange_*: rows stored straight into every rank's region, arrival flags,
+    no collective call): `world` sharded sessions of ONE process on one GPU, wired with
+    fpb200_exchange_connect_local, each run the public register_async; every rank must return the unsharded
+    session's winner, scores and pose bit for bit - eagerly, while capturing, and from the replayed CUDA graph
+    (the exchange is double-buffered by epoch parity, so back-to-back calls are covered too)."""
+    ms = [setup["make"](r, world) for r in range(world)]
+    try:
+        api.connect_local(ms)
+        for m in ms:
+            m.upload(setup["rgb"], setup["depth"])
+            m.sample_hypotheses(setup["mask"], "obj")
+        for rep in range(4):
+            for m in ms:
+                m.register_async("obj", 1)
+            for m in ms:
+                idx, pose = m.wait()
+                assert idx == int(np.argmax(setup["scores"])), (rep, idx)
+                assert np.array_equal(pose, setup["pose"])
+                assert np.array_equal(m.read_buffer("scores", np.float32, N), setup["scores"])
+        # a rank that skips a call is reported, not waited for forever
+        ms[0].register_async("obj", 1)
+        with pytest.raises(Exception) as e:
+            ms[0].wait()
+        assert "exchange timed out" in str(e.value)
+    finally:
+        for m in ms:
+            m.close()
