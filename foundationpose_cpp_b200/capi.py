@@ -39,6 +39,12 @@ class ConvDesc(C.Structure):
     ]
 
 
+class EncoderDesc(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("att", "x0", "w_out", "w1", "w2", "b_out", "b1", "b2", "ln1_g", "ln1_b",
+                                          "ln2_g", "ln2_b", "partial", "mean_out")] + \
+               [("n_hyp", C.c_int), ("mode", C.c_int)] + [(n, C.c_void_p) for n in ("dbg_x1", "dbg_h", "dbg_y")]
+
+
 class Mesh(C.Structure):
     _fields_ = [
         ("name", C.c_char_p),
@@ -75,6 +81,12 @@ def check(code: int) -> None:
 def debug_conv_gemm(desc: ConvDesc, repeat: int = 0) -> float:
     ms = C.c_float(0)
     check(lib().fpb200_debug_conv_gemm(C.byref(desc), C.c_int(repeat), C.byref(ms)))
+    return ms.value
+
+
+def debug_encoder_block(desc: EncoderDesc, repeat: int = 0) -> float:
+    ms = C.c_float(0)
+    check(lib().fpb200_debug_encoder_block(C.byref(desc), C.c_int(repeat), C.byref(ms)))
     return ms.value
 
 

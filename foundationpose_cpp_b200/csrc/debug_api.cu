@@ -7,6 +7,7 @@
 #include "../../include/fpb200.h"
 #include "common.h"
 #include "conv_gemm.h"
+#include "encoder_block.h"
 #include "net_ops.h"
 
 using namespace fpb;
@@ -141,3 +142,22 @@ extern "C" int fpb200_debug_attention_phases(unsigned long long out[22]) {
 }
 
 extern "C" const char* fpb200_last_error(void) { return last_error().c_str(); }
+
+extern "C" int fpb200_debug_encoder_block(const fpb200_encoder_desc* c, int repeat, float* ms_out) {
+  if (!c) return fail(FPB200_ERR_INVALID, "null descriptor");
+  EncoderBlockDesc d;
+  d.att = static_cast<const __half*>(c->att);
+  d.x0 = static_cast<const __half*>(c->x0);
+  d.w_out = static_cast<const __half*>(c->w_out);
+  d.w1 = static_cast<const __half*>(c->w1);
+  d.w2 = static_cast<const __half*>(c->w2);
+  d.b_out = c->b_out; d.b1 = c->b1; d.b2 = c->b2;
+  d.ln1_g = c->ln1_g; d.ln1_b = c->ln1_b; d.ln2_g = c->ln2_g; d.ln2_b = c->ln2_b;
+  d.partial = c->partial; d.mean_out = c->mean_out; d.n_hyp = c->n_hyp; d.mode = c->mode;
+  d.dbg_x1 = static_cast<__half*>(c->dbg_x1);
+  d.dbg_h = static_cast<__half*>(c->dbg_h);
+  d.dbg_y = static_cast<__half*>(c->dbg_y);
+  EncoderBlockPlan plan;
+  if (const char* e = build_encoder_block(d, &plan)) return fail(FPB200_ERR_INVALID, "%s", e);
+  return timed_launches([&]() { FPB_CUDA(launch_encoder_block(plan, 0)); }, repeat, ms_out);
+}

@@ -2,10 +2,12 @@
 #include "network.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 
 #include "common.h"
+#include "encoder_block.h"
 #include "net_ops.h"
 
 namespace fpb {
@@ -85,7 +87,7 @@ Arena::Arena(int max_hyps) : cap(max_hyps) {
       {(void**)&qkv, 3 * tok}, {(void**)&att, tok}, {(void**)&proj, tok}, {(void**)&x1, tok},
       {(void**)&ff1, tok}, {(void**)&ff2, tok}, {(void**)&x2, tok},
       {(void**)&mean_t, n * 512 * 4}, {(void**)&mean_r, n * 512 * 4},
-      {(void**)&mean_part, (size_t)n * kLnMeanSlices * 512 * 4},
+      {(void**)&mean_part, (size_t)n * 25 * 512 * 4},  // 25 group sums of 16 tokens per hypothesis (>= 8 slices)
   };
   size_t total = 0;
   for (auto& it : items) total += (it.bytes + 1023) / 1024 * 1024;
@@ -107,8 +109,9 @@ Arena::~Arena() {
 // ------------------------------------------------------------------ network
 struct Network::Plan {
   std::vector<std::function<void(cudaStream_t)>> steps;
-  std::vector<double> gemm_flops;  // per step; 0 for non-GEMM steps
+  std::vector<double> gemm_flops;  // per step; 0 for steps that are not conv_gemm launches
   double flops = 0;
+  int launches = 0;                // kernel launches of one forward
 };
 
 Network::Network(NetKind kind, const std::string& weight_path, Arena* arena)
@@ -116,6 +119,7 @@ Network::Network(NetKind kind, const std::string& weight_path, Arena* arena)
   if (const char* e = conv_gemm_init()) throw std::runtime_error(e);
   if (const char* e = attention_init()) throw std::runtime_error(e);
   if (const char* e = net_ops_init()) throw std::runtime_error(e);
+  if (const char* e = encoder_block_init()) throw std::runtime_error(e);
   flops_per_hyp_ = plan(1).flops;
 }
 
@@ -215,15 +219,34 @@ void Network::add_encoder_layer(Plan& p, int n, const std::string& h, float* mea
   add_gemm(p.steps, &p.flops, linear_desc(A.d0, rows, 512, W.f16(h + ".qkv.w", 1536, 512), W.f32(h + ".qkv.b", 1536), 1536, A.qkv, false));
   add_attention(p.steps, A.qkv, A.att, n);
   p.flops += 2.0 * n * 4 * 2 * 400.0 * 400.0 * 128.0;
-  // post-LN encoder layer: the two residual sums are formed in the GEMM epilogues
-  add_gemm(p.steps, &p.flops, linear_desc(A.att, rows, 512, W.f16(h + ".out.w", 512, 512), W.f32(h + ".out.b", 512), 512, A.proj, false, A.d0));
   const float *g1 = W.f32(h + ".ln1.g", 512), *b1 = W.f32(h + ".ln1.b", 512);
-  p.steps.push_back([&A, rows, g1, b1](cudaStream_t s) { launch_layernorm(A.proj, g1, b1, A.x1, rows, s); });
-  add_gemm(p.steps, &p.flops, linear_desc(A.x1, rows, 512, W.f16(h + ".ff1.w", 512, 512), W.f32(h + ".ff1.b", 512), 512, A.ff1, true));
-  add_gemm(p.steps, &p.flops, linear_desc(A.ff1, rows, 512, W.f16(h + ".ff2.w", 512, 512), W.f32(h + ".ff2.b", 512), 512, A.ff2, false, A.x1));
   const float *g2 = W.f32(h + ".ln2.g", 512), *b2 = W.f32(h + ".ln2.b", 512);
-  // the second LayerNorm's tokens are consumed only through their mean: fused, never stored
-  p.steps.push_back([&A, n, g2, b2, mean_out](cudaStream_t s) { launch_layernorm_mean(A.ff2, g2, b2, mean_out, n, A.mean_part, s); });
+  static const bool unfused = getenv("FPB200_UNFUSED_ENCODER") != nullptr;  // A/B measurements only
+  if (!unfused) {
+    // out-projection + residual + LayerNorm1 + FFN + residual + LayerNorm2 + token mean: one kernel that keeps
+    // each 128-token row block on chip through the three GEMMs (encoder_block.cu)
+    EncoderBlockDesc d;
+    d.att = A.att; d.x0 = A.d0; d.n_hyp = n;
+    d.w_out = W.f16(h + ".out.w", 512, 512); d.b_out = W.f32(h + ".out.b", 512);
+    d.w1 = W.f16(h + ".ff1.w", 512, 512); d.b1 = W.f32(h + ".ff1.b", 512);
+    d.w2 = W.f16(h + ".ff2.w", 512, 512); d.b2 = W.f32(h + ".ff2.b", 512);
+    d.ln1_g = g1; d.ln1_b = b1; d.ln2_g = g2; d.ln2_b = b2;
+    d.partial = A.mean_part; d.mean_out = mean_out;
+    EncoderBlockPlan ep;
+    if (const char* e = build_encoder_block(d, &ep)) throw std::runtime_error(e);
+    p.flops += ep.flops;
+    p.steps.push_back([ep](cudaStream_t s) { FPB_CUDA(launch_encoder_block(ep, s)); });
+    p.launches += 1;  // the step launches two kernels
+  } else {
+    // post-LN encoder layer, layer by layer: the two residual sums are formed in the GEMM epilogues
+    add_gemm(p.steps, &p.flops, linear_desc(A.att, rows, 512, W.f16(h + ".out.w", 512, 512), W.f32(h + ".out.b", 512), 512, A.proj, false, A.d0));
+    p.steps.push_back([&A, rows, g1, b1](cudaStream_t s) { launch_layernorm(A.proj, g1, b1, A.x1, rows, s); });
+    add_gemm(p.steps, &p.flops, linear_desc(A.x1, rows, 512, W.f16(h + ".ff1.w", 512, 512), W.f32(h + ".ff1.b", 512), 512, A.ff1, true));
+    add_gemm(p.steps, &p.flops, linear_desc(A.ff1, rows, 512, W.f16(h + ".ff2.w", 512, 512), W.f32(h + ".ff2.b", 512), 512, A.ff2, false, A.x1));
+    // the second LayerNorm's tokens are consumed only through their mean: fused, never stored
+    p.steps.push_back([&A, n, g2, b2, mean_out](cudaStream_t s) { launch_layernorm_mean(A.ff2, g2, b2, mean_out, n, A.mean_part, s); });
+    if (n < 128) p.launches += 1;  // sliced LayerNorm + mean: two kernels
+  }
   p.flops += 2.0 * n * 512 * 3;  // Linear(512,3) on the token mean
 }
 
@@ -250,6 +273,7 @@ Network::Plan& Network::plan(int n) {
   }
   g_gemm_flops_sink = nullptr;
   p->gemm_flops.resize(p->steps.size(), 0.0);
+  p->launches += (int)p->steps.size();
   p->flops /= n;
   Plan& ref = *p;
   plans_[n] = std::move(p);
@@ -297,9 +321,6 @@ void Network::collect_profile(double* ms, double* flops, long long* launches) {
   ev_flops_.clear();
 }
 
-int Network::launches_per_forward(int n) {
-  // the LayerNorm + token mean of the two refiner heads is two kernels per step for few hypotheses
-  return (int)plan(n).steps.size() + (kind_ == NetKind::kRefiner && n < 128 ? 2 : 0);
-}
+int Network::launches_per_forward(int n) { return plan(n).launches; }
 
 }  // namespace fpb

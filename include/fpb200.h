@@ -222,6 +222,21 @@ int fpb200_debug_attention(const void* qkv, void* out, int n_hyp, int repeat, fl
  * 2 unused, then 6 sums of the MMA-issuing thread {wait Q, wait K, wait O drained, wait V, wait P steps, issue}. */
 int fpb200_debug_attention_phases(unsigned long long out[22]);
 
+/* Fused tail of one transformer encoder layer of the refiner (inside the TensorRT engine in the reference):
+ * att, x0 [n_hyp*400, 512] fp16 -> mean_out [n_hyp, 512] f32 = token mean of
+ * LayerNorm2(x1 + FFN(x1)), x1 = LayerNorm1(x0 + att Wout^T + b_out).  Weights [512][512] fp16 (out x in),
+ * biases / LayerNorm parameters f32 [512]; partial: n_hyp*25*512 floats of scratch; dbg_*: optional
+ * [n_hyp*400, 512] fp16 dumps of LayerNorm1 output, FFN activation, LayerNorm2 output.
+ * mode: 0 automatic, 1 single CTAs, 2 CTA pairs. */
+typedef struct {
+  const void *att, *x0, *w_out, *w1, *w2;
+  const float *b_out, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  float *partial, *mean_out;
+  int n_hyp, mode;
+  void *dbg_x1, *dbg_h, *dbg_y;
+} fpb200_encoder_desc;
+int fpb200_debug_encoder_block(const fpb200_encoder_desc* desc, int repeat, float* ms_out);
+
 /* fp32 operators of the scorer tail (after the token mean; inside the scorer engine in the reference):
  * out[rows, outs] = in[rows, k] w[outs, k]^T + b (b may be NULL), and the cross-hypothesis attention
  * qkv [n, 1536] (Q | K | V, 4 heads x 128) -> out [n, 512].  Once + `repeat` timed launches. */
