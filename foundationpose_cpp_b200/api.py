@@ -85,7 +85,7 @@ class FoundationPose:
 
     def __init__(self, refiner_weights: str, scorer_weights: str, mesh_loaders: Sequence[BaseMeshLoader], K,
                  max_h: int = 1080, max_w: int = 1920, device: int = 0, max_hyps: int = 252, shard_rank: int = 0,
-                 shard_world: int = 1):
+                 shard_world: int = 1, use_cuda_graph: bool = True):
         self._lib = capi.lib()
         self._keep = []
         meshes = (capi.Mesh * len(mesh_loaders))()
@@ -111,6 +111,7 @@ class FoundationPose:
         opts = capi.Options()
         self._lib.fpb200_default_options(C.byref(opts))
         opts.device, opts.max_hyps, opts.shard_rank, opts.shard_world = device, max_hyps, shard_rank, shard_world
+        opts.use_cuda_graph = int(bool(use_cuda_graph))
         self._h = C.c_void_p()
         capi.check(self._lib.fpb200_create(meshes, len(mesh_loaders), _fptr(self._K), max_h, max_w,
                                             refiner_weights.encode(), scorer_weights.encode(), C.byref(opts),
@@ -249,6 +250,12 @@ class FoundationPose:
     def debug_options(self, rast_ids: bool = False, render_split: int = -1):
         """Test switches (fpb200_debug_options): write the visibility id map, force a render path."""
         capi.check(self._lib.fpb200_debug_options(self._h, int(bool(rast_ids)), int(render_split)))
+
+    def time_stage(self, stage: int, repeat: int = 20) -> float:
+        """Average device ms of one stage (0 render, 1 warp, 2 exchange) on the current hypotheses."""
+        ms = C.c_float(0)
+        capi.check(self._lib.fpb200_debug_time_stage(self._h, int(stage), int(repeat), C.byref(ms)))
+        return ms.value
 
     def last_timings(self) -> List[float]:
         ms = (C.c_float * 8)()

@@ -1112,6 +1112,50 @@ int fpb200_exchange_connect_local(fpb200_session* const* sessions, int world) {
   });
 }
 
+int fpb200_debug_time_stage(fpb200_session* s, int stage, int repeat, float* ms_out) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && ms_out && repeat >= 1, "bad argument");
+    if (!s->uploaded || !s->cur_mesh || s->n_hyp <= 0) return fail(FPB200_ERR_STATE, "upload an image and set hypotheses first");
+    const int nl = s->hi - s->lo;
+    const MeshEntry& m = *s->cur_mesh;
+    auto run = [&]() {
+      switch (stage) {
+        case FPB200_STAGE_RENDER:
+          launch_pose_setup(s->poses.p + 16 * s->lo, nl, s->intr, m.dm.diameter, kRefineCropRatio, s->aux.p, s->stream);
+          launch_render(m.dm, s->aux.p, nl, s->vclip.p, s->vattr.p, s->arena->packed, 0, nullptr, s->status.p, s->zbuf.p,
+                        kSplitRenderPoses, s->num_sms, s->render_split, s->stream);
+          break;
+        case FPB200_STAGE_WARP:
+          launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->stream);
+          break;
+        case FPB200_STAGE_EXCHANGE:
+          FPB_REQUIRE(s->exchange_ready, "the exchange is not connected");
+          exchange_begin_kernel<<<1, 1, 0, s->stream>>>(s->peers.epoch);
+          exchange_push_kernel<<<s->peers.world, 1024, 0, s->stream>>>(s->peers, s->feats.p, s->poses.p + 16 * s->lo, s->lo, nl);
+          exchange_collect_kernel<<<16, 256, 0, s->stream>>>(s->peers, s->feats.p, s->all_poses.p, s->n_hyp, s->status.p);
+          break;
+        default:
+          throw std::invalid_argument("unknown stage");
+      }
+      FPB_CUDA(cudaGetLastError());
+    };
+    run();  // warm-up
+    cudaEvent_t e0, e1;
+    FPB_CUDA(cudaEventCreate(&e0));
+    FPB_CUDA(cudaEventCreate(&e1));
+    FPB_CUDA(cudaEventRecord(e0, s->stream));
+    for (int i = 0; i < repeat; ++i) run();
+    FPB_CUDA(cudaEventRecord(e1, s->stream));
+    FPB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    FPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_out = ms / repeat;
+    return FPB200_OK;
+  });
+}
+
 int fpb200_debug_options(fpb200_session* s, int write_rast_ids, int render_split) {
   return guard([&]() -> int {
     FPB_REQUIRE(s, "null session");

@@ -148,6 +148,12 @@ int fpb200_read_buffer(fpb200_session* s, const char* name, void* host_dst, size
  * (band, hypothesis) on shared-memory z-buffers, 1 = triangles spread over all SMs on global z-buffers
  * (what few-hypothesis launches use); both give identical ids.  Drops captured CUDA graphs. */
 int fpb200_debug_options(fpb200_session* s, int write_rast_ids, int render_split);
+/* Average device time (ms, CUDA events on the session stream) of `repeat` runs of one stage on the session's
+ * current hypotheses: RENDER = pose set-up + vertex stage + rasterise + shade + pack (refine crop ratio; what
+ * the reference does in RenderProcess, fp/src/foundationpose_render.cpp:685-729), WARP = observed crop
+ * (TransfProcess, :731-812), EXCHANGE = the peer-memory exchange alone (all ranks must call it together). */
+enum { FPB200_STAGE_RENDER = 0, FPB200_STAGE_WARP = 1, FPB200_STAGE_EXCHANGE = 2 };
+int fpb200_debug_time_stage(fpb200_session* s, int stage, int repeat, float* ms_out);
 /* Device-side duration of the stages of the last Register/Track (CUDA events), in ms:
  * [0] upload+xyz [1] sampler [2] unused [3] refine iterations (render, warp, net, pose update)
  * [4] score preprocess + scorer net [5] scorer tail + argmax [6] unused; returns the number filled. */

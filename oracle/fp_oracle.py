@@ -306,6 +306,36 @@ def build_c_oracle(force: bool = False) -> Path:
     return so
 
 
+_HOST_LIB = None
+
+
+def host_prepost_lib():
+    """oracle/host_prepost.cpp -> oracle/libhost_prepost.so: the reference's host-side functions of the path
+    (GuessTranslation, crop window, bbox2d, projection, RefinePostProcess) in dependency-free C++, for the CPU
+    baseline timing.  Checked against this file by tests/test_oracle.py."""
+    global _HOST_LIB
+    if _HOST_LIB is None:
+        so, src = HERE / "libhost_prepost.so", HERE / "host_prepost.cpp"
+        if not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-o", str(so),
+                            str(src)], check=True)
+        _HOST_LIB = ctypes.CDLL(str(so))
+        _HOST_LIB.host_register_work_ms.restype = ctypes.c_double
+    return _HOST_LIB
+
+
+def host_register_work_ms(depth, mask, K, grid_poses, diameter, refine_itr=1, threads=1, repeat=20):
+    """Milliseconds of the reference's host-side work for one Register (see host_prepost.cpp)."""
+    lib = host_prepost_lib()
+    depth = np.ascontiguousarray(depth, F)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    Kf = np.ascontiguousarray(np.asarray(K, F).reshape(9))
+    poses = np.ascontiguousarray(np.asarray(grid_poses, F).reshape(-1, 16))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    return float(lib.host_register_work_ms(p(depth), p(mask), depth.shape[0], depth.shape[1], p(Kf), p(poses),
+                                           poses.shape[0], ctypes.c_float(diameter), refine_itr, threads, repeat))
+
+
 def rasterize_ids(clip, faces, h=CROP, w=CROP):
     """cudaraster visibility (oracle/raster_oracle.c).  Returns (ids [h,w] i32 with row 0 = GL
     bottom row, number of triangles that took cudaraster's polygon clipper)."""

@@ -2,6 +2,7 @@
 (oracle/_ref/libref_kernels.so, built from /root/reference by oracle/Makefile) on seeded inputs.
 Run on a GPU box:   python tests/golden/make_golden.py gpurun_out/ref_kernels_golden.npz
                     python tests/golden/make_golden.py clip gpurun_out/ref_clip_golden.npz
+                    python tests/golden/make_golden.py render gpurun_out/ref_render_golden.npz
 The inputs are stored next to the outputs so the CPU oracle can be checked without a GPU."""
 import ctypes as C
 import os
@@ -125,8 +126,69 @@ def main(out_path):
     print("wrote", out_path, os.path.getsize(out_path), "bytes; coverage", float((rast[..., 3] > 0).mean()))
 
 
+def render_inputs():
+    """Inputs of the reference's render sequence (ref_render_sequence in oracle/ref_render_shim.cu): 4 hypotheses
+    of the small golden mesh, with the host-side matrices the reference computes in
+    GeneratePoseClipOnCUDA / ConstructBBox2D (foundationpose_render.cpp:123-186,570-609) taken from the oracle."""
+    mesh = synth.uv_ellipsoid("g", slices=24, stacks=13, tex_size=64, seed=5)
+    rgb, depth, mask, gt = synth.make_scene(mesh)
+    om = helpers.oracle_mesh(mesh)
+    K = synth.DEFAULT_K
+    poses = np.concatenate([gt[None], O.sample_hypotheses(depth, mask, K)[[0, 77, 190]]], 0).astype(np.float32)
+    tfs, _ = O.crop_window_tf(poses, K, 1.2, om["diameter"])
+    bbox = O.bbox2d_from_tf(tfs)
+    proj = O.projection_matrix(K, 480, 640)
+    mvp = np.stack([O._mat4_mul(proj, O._mat4_mul(O.GL_CAM_IN_CV_CAM, p)) for p in poses]).astype(np.float32)
+    return {"poses": poses, "mvp": mvp, "bbox2d": bbox.astype(np.float32), "vertices": om["vertices"],
+            "normals": om["normals"], "texcoords": om["texcoords"], "faces": om["faces"], "texture": om["texture"],
+            "diameter": np.float32(om["diameter"]), "K": np.asarray(K, np.float32)}
+
+
+def run_render_sequence(g, repeat=0):
+    """Runs the reference's render path on the GPU; returns its buffers as numpy arrays (+ avg ms if repeat > 0)."""
+    lib = ref_lib()
+    n, v, t = g["poses"].shape[0], g["vertices"].shape[0], g["faces"].shape[0]
+    th, tw, _ = g["texture"].shape
+    H = W = 160
+    col_major = lambda m: np.ascontiguousarray(m.transpose(0, 2, 1)).reshape(n, 16)
+    d = {k: dev(a) for k, a in (("pose", col_major(g["poses"])), ("mvp", col_major(g["mvp"])), ("bbox", g["bbox2d"]),
+                                ("verts", g["vertices"]), ("normals", g["normals"]), ("tc", g["texcoords"]),
+                                ("faces", g["faces"]), ("tex", g["texture"]))}
+    out = {"pts_cam": torch.zeros(n, v, 3, device="cuda"), "pose_clip": torch.zeros(n, v, 4, device="cuda"),
+           "diffuse": torch.zeros(n, v, device="cuda"), "rast": torch.zeros(n, H, W, 4, device="cuda"),
+           "xyz_map": torch.zeros(n, H, W, 3, device="cuda"), "uv": torch.zeros(n, H, W, 2, device="cuda"),
+           "color": torch.zeros(n, H, W, 3, device="cuda"), "diffuse_map": torch.zeros(n, H, W, device="cuda"),
+           "render_input": torch.zeros(n, H, W, 6, device="cuda")}
+    ms = C.c_float(0)
+    lib.ref_render_sequence.argtypes = [C.c_void_p] * 17 + [C.c_int] * 9 + [C.c_float, C.c_int, C.c_void_p]
+    rc = lib.ref_render_sequence(ptr(d["pose"]), ptr(d["mvp"]), ptr(d["bbox"]), ptr(d["verts"]), ptr(d["normals"]),
+                                 ptr(d["tc"]), ptr(d["faces"]), ptr(d["tex"]), ptr(out["pts_cam"]), ptr(out["pose_clip"]),
+                                 ptr(out["diffuse"]), ptr(out["rast"]), ptr(out["xyz_map"]), ptr(out["uv"]),
+                                 ptr(out["color"]), ptr(out["diffuse_map"]), ptr(out["render_input"]), v, t, th, tw, n,
+                                 H, W, 480, 640, float(g["diameter"]), repeat, C.byref(ms))
+    assert rc == 0, rc
+    res = {k: a.cpu().numpy() for k, a in out.items()}
+    res["ms"] = ms.value
+    return res
+
+
+def main_render(out_path):
+    """tests/golden/ref_render_golden.npz: outputs of the reference's own foundationpose_render.cu kernels
+    (K4 transform_points, K5 generate_pose_clip, K6 transform_normals, K14 refine_color, K15 clamp,
+    K16 threshold_and_downscale_pointcloud, K17 concat) chained as in NvdiffrastRender + RenderProcess."""
+    g = render_inputs()
+    r = run_render_sequence(g)
+    sub = (slice(None), slice(0, 160, 4), slice(0, 160, 4))
+    np.savez_compressed(out_path, **g, ref_pts_cam=r["pts_cam"], ref_pose_clip=r["pose_clip"], ref_diffuse=r["diffuse"],
+                        ref_ids=r["rast"][..., 3].astype(np.int16), ref_color_sub=r["color"][sub],
+                        ref_render_input_sub=r["render_input"][sub])
+    print("wrote", out_path, os.path.getsize(out_path), "bytes; coverage", float((r["rast"][..., 3] > 0).mean()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "clip":
         main_clip(sys.argv[2])
+    elif len(sys.argv) > 2 and sys.argv[1] == "render":
+        main_render(sys.argv[2])
     else:
         main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", "ref_kernels_golden.npz"))

@@ -46,6 +46,33 @@ def test_shader_interpolate_texture_match_nvdiffrast():
         np.testing.assert_allclose(col[SUB], G["ref_col_sub"][i], atol=2e-4)
 
 
+def test_vertex_stage_and_shading_match_reference_render_kernels():
+    """tests/golden/ref_render_golden.npz (make_golden.py render): outputs of the reference's own
+    foundationpose_render.cu kernels K4 / K5 / K6 (vertex stage) and K14-K17 (shading, clamp, normalise, concat)
+    chained as in NvdiffrastRender, generated on a B200.  The oracle restates each of them
+    (detection_6d_foundationpose/src/foundationpose_render.cu:61-140,321-501)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_render_golden.npz")
+    g = np.load(path)  # committed; regenerate with `python tests/golden/make_golden.py render <out>` on a GPU box
+    eps = np.finfo(np.float32).eps
+    mesh = {"vertices": g["vertices"], "normals": g["normals"], "texcoords": g["texcoords"], "faces": g["faces"],
+            "texture": g["texture"], "diameter": float(g["diameter"])}
+    for i in range(g["poses"].shape[0]):
+        pts = O.transform_points(g["vertices"], g["poses"][i])
+        clip = O.clip_vertices(g["vertices"], g["poses"][i], g["bbox2d"][i], g["K"], 480, 640)
+        dif = O.diffuse_intensity(g["normals"], g["poses"][i])
+        # the reference build contracts the row sums into FMAs; the oracle rounds every product: <= a few ulp
+        assert np.abs(pts - g["ref_pts_cam"][i]).max() <= 4 * eps * max(1.0, np.abs(g["ref_pts_cam"][i]).max())
+        assert np.abs(clip - g["ref_pose_clip"][i]).max() <= 4 * eps * max(1.0, np.abs(g["ref_pose_clip"][i]).max())
+        assert np.abs(dif - g["ref_diffuse"][i]).max() <= 4 * eps
+        ids, _ = O.rasterize_ids(clip, g["faces"])
+        assert np.array_equal(ids, g["ref_ids"][i].astype(np.int32))
+        tfs, _ = O.crop_window_tf(g["poses"][i:i + 1], g["K"], 1.2, mesh["diameter"])
+        col, xyz, _, _ = O.render_crop(mesh, g["poses"][i], tfs[0], g["K"], 480, 640)
+        packed = O.normalize_pack(col, xyz, g["poses"][i], mesh["diameter"])
+        # reference rows are in GL order (its two cvcuda::Flip calls are CV-CUDA, absent here): un-flip the oracle
+        np.testing.assert_allclose(packed[::-1][SUB], g["ref_render_input_sub"][i], atol=2e-4)
+
+
 def test_depth_kernels_match_reference():
     np.testing.assert_array_equal(O.erode_depth(G["depth_patch"]), G["ref_eroded"])
     np.testing.assert_allclose(O.bilateral_filter_depth(G["ref_eroded"]), G["ref_filtered"], rtol=2e-6, atol=1e-7)

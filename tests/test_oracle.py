@@ -254,3 +254,40 @@ def test_clipper_agrees_with_double_precision_clipping():
         drawn += int((ids > 0).sum())
         assert diff <= 0.02 * max(1, (ids2 > 0).sum()) + 3, diff
     assert drawn > 2000, "the random triangles must cover something"
+
+
+def test_host_prepost_cpp_matches_the_numpy_oracle():
+    """oracle/host_prepost.cpp (the reference's host-side functions in dependency-free C++, timed as part of the CPU
+    baseline) against fp_oracle.py on a seeded scene: translation guess, crop transforms, bbox2d, clip matrices and
+    the pose update must be the same numbers."""
+    import ctypes
+    from foundationpose_cpp_b200 import synth
+    lib = O.host_prepost_lib()
+    mesh = synth.uv_ellipsoid("m", slices=16, stacks=9, tex_size=32, seed=2)
+    rgb, depth, mask, gt = synth.make_scene(mesh)
+    K = synth.DEFAULT_K
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    Kf = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
+    c = np.zeros(3, np.float32)
+    assert lib.host_guess_translation(p(np.ascontiguousarray(depth, np.float32)), p(np.ascontiguousarray(mask)), 480, 640, p(Kf), p(c)) == 0
+    np.testing.assert_allclose(c, O.guess_translation(depth, mask, K), rtol=1e-6)
+    assert lib.host_guess_translation(p(np.ascontiguousarray(depth, np.float32)), p(np.zeros_like(mask)), 480, 640, p(Kf), p(c)) != 0
+    poses = O.rotation_grid()[::17].copy()
+    poses[:, :3, 3] = c
+    n = len(poses)
+    flat = np.ascontiguousarray(poses.reshape(n, 16), np.float32)
+    tf, bbox, mvp = np.zeros((n, 9), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 16), np.float32)
+    lib.host_pose_setup(p(flat), n, p(Kf), 480, 640, ctypes.c_float(mesh.diameter), ctypes.c_float(1.2), p(tf), p(bbox), p(mvp))
+    ref_tf, _ = O.crop_window_tf(poses, K, 1.2, mesh.diameter)
+    np.testing.assert_array_equal(tf.reshape(n, 3, 3), ref_tf)
+    np.testing.assert_array_equal(bbox, O.bbox2d_from_tf(ref_tf))
+    proj = O.projection_matrix(K, 480, 640)
+    for i in range(n):
+        np.testing.assert_array_equal(mvp[i].reshape(4, 4), O._mat4_mul(proj, O._mat4_mul(O.GL_CAM_IN_CV_CAM, poses[i])))
+    rng = np.random.default_rng(0)
+    trans, rot = rng.normal(0, 0.2, (n, 3)).astype(np.float32), rng.normal(0, 0.5, (n, 3)).astype(np.float32)
+    upd = flat.copy()
+    lib.host_refine_post(p(upd), n, p(trans), p(rot), ctypes.c_float(mesh.diameter))
+    np.testing.assert_allclose(upd.reshape(n, 4, 4), O.pose_update(poses, trans, rot, mesh.diameter), atol=2e-6)
+    ms1 = O.host_register_work_ms(depth, mask, K, O.rotation_grid(), mesh.diameter, threads=1, repeat=3)
+    assert 0 < ms1 < 1000

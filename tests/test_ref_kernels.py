@@ -123,3 +123,61 @@ def test_polygon_clipper_matches_reference_cudaraster(tmp_path):
         assert d == 0, f"product (split={split}): {d} visibility ids differ from cudaraster"
         assert model.read_buffer("status", np.int32, 1)[0] & 4, "the clip-path flag must be raised"
     model.close()
+
+
+def test_render_sequence_matches_reference_render_kernels(tmp_path):
+    """The reference's own foundationpose_render.cu kernels (K4-K6, K14-K17; compiled in place into oracle/_ref)
+    chained as in NvdiffrastRender + RenderProcess, against (a) the oracle's restatement of each of them and
+    (b) the product's fused render kernel, on the same hypotheses.  Bars: vertex stage bit-exact (the same fp32
+    expressions; nvcc contracts a*x + b*y + c*z + d into FMAs in the reference build, so <= 2 ulp is allowed and the
+    maximum is recorded), ids identical, packed render_input within fp16 rounding of the reference's fp32 output."""
+    import fp_helpers as helpers
+    from conftest import record_err
+    from foundationpose_cpp_b200 import api, synth
+    from oracle import fp_oracle as O
+    mk = _mk()
+    g = mk.render_inputs()
+    r = mk.run_render_sequence(g)
+    n = g["poses"].shape[0]
+    # (a) oracle restatement of the vertex-stage kernels
+    for i in range(n):
+        pts = O.transform_points(g["vertices"], g["poses"][i])
+        clip = O.clip_vertices(g["vertices"], g["poses"][i], g["bbox2d"][i], g["K"], 480, 640)
+        dif = O.diffuse_intensity(g["normals"], g["poses"][i])
+        for name, got, ref in (("K4 transform_points", pts, r["pts_cam"][i]), ("K5 generate_pose_clip", clip, r["pose_clip"][i]),
+                               ("K6 transform_normals", dif, r["diffuse"][i])):
+            err = float(np.abs(got - ref).max())
+            tol = 4 * np.finfo(np.float32).eps * max(1.0, float(np.abs(ref).max()))
+            record_err(f"ref render kernels/oracle {name} [{i}]", err, tol)
+            assert err <= tol, (name, err)
+    # (b) the product on the same hypotheses
+    mesh = synth.uv_ellipsoid("g", slices=24, stacks=13, tex_size=64, seed=5)
+    rgb, depth, mask, gt = synth.make_scene(mesh)
+    rp, sp = helpers.write_seeded_weights(str(tmp_path))
+    model = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], synth.DEFAULT_K, 480, 640)
+    model.debug_options(rast_ids=True)
+    model.upload(rgb, depth)
+    model.set_hypotheses(g["poses"], "g")
+    model.render_and_transform(1.2)
+    ids = model.read_buffer("rast_id", np.int32, n * 160 * 160).reshape(n, 160, 160)
+    ref_ids = r["rast"][..., 3].astype(np.int32)
+    assert int((ids != ref_ids).sum()) == 0
+    got = model.read_packed("render_input", n)
+    ref = r["render_input"][:, ::-1]  # the two cvcuda::Flip calls of the reference (CV-CUDA is absent)
+    ref16 = ref.astype(np.float16).astype(np.float32)
+    diff = np.abs(got - ref16)
+    ulp = np.maximum(np.abs(ref16), 2.0 ** -14) * 2.0 ** -10
+    # the reference build contracts fp32 expressions into FMAs, the product (like the oracle) rounds every operation:
+    # barycentrics / texture colours then differ by up to ~4e-4 (edge-function cancellation), i.e. up to 2 fp16 steps
+    record_err("ref render kernels/product render_input vs reference fp32 output (fp16 ulps)", float((diff / ulp).max()), 2.5)
+    record_err("ref render kernels/product render_input: fraction of elements that differ", float((diff > 0).mean()), 1e-2)
+    assert np.all(diff <= 2.5 * ulp), float((diff / ulp).max())
+    assert float((diff > 0).mean()) <= 1e-2
+    assert float((diff > 1.001 * ulp).mean()) <= 1e-4
+    # the oracle's full render (what every other test compares the product with) against the same reference output
+    xyz_map = O.depth_to_xyz(depth, synth.DEFAULT_K)
+    ren, _, _ = O.render_and_transform(helpers.oracle_mesh(mesh), g["poses"], rgb, xyz_map, synth.DEFAULT_K, 1.2)
+    err = float(np.abs(ren - ref).max())
+    record_err("ref render kernels/oracle render_input vs reference", err, 2e-4)
+    assert err <= 2e-4
+    model.close()
