@@ -33,7 +33,27 @@ class BaseMeshLoader:
     def GetMeshTextureCoords(self) -> np.ndarray: raise NotImplementedError
     def GetMeshTriangleFaces(self) -> np.ndarray: raise NotImplementedError
     def GetMeshModelCenter(self) -> np.ndarray: raise NotImplementedError
+    def GetOrientBounds(self) -> np.ndarray: raise NotImplementedError
+    def GetObjectDimension(self) -> np.ndarray: raise NotImplementedError
     def GetTextureMap(self) -> np.ndarray: raise NotImplementedError
+
+
+def compute_obb(vertices: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """ComputeOBB (assimp_mesh_loader.cpp:62-113): PCA of the vertex cloud.  Returns (orient_bounds 4x4, dimension 3):
+    rotation = eigenvectors of the vertex covariance in ASCENDING eigenvalue order (Eigen's SelfAdjointEigenSolver
+    convention, which numpy.linalg.eigh shares), translation = vertex mean, dimension = extent of the vertices along
+    those axes.  The sign of each eigenvector is the solver's choice in the reference too (not pinned)."""
+    v = np.asarray(vertices, np.float32)
+    mean = v.sum(0, dtype=np.float32) / np.float32(len(v))
+    diff = v - mean
+    cov = (diff.T @ diff) / np.float32(len(v))
+    _, rot = np.linalg.eigh(cov.astype(np.float32))
+    rot = rot.astype(np.float32)
+    tf = np.eye(4, dtype=np.float32)
+    tf[:3, :3] = rot
+    tf[:3, 3] = mean
+    proj = v @ rot  # rows = rotation^T * vertex
+    return tf, (proj.max(0) - proj.min(0)).astype(np.float32)
 
 
 class ArrayMeshLoader(BaseMeshLoader):
@@ -54,6 +74,7 @@ class ArrayMeshLoader(BaseMeshLoader):
             d2 = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
             diameter = float(np.sqrt(d2.max()))
         self._d = float(diameter)
+        self._obb, self._dim = compute_obb(self._v)
 
     @classmethod
     def from_mesh_data(cls, m):
@@ -66,14 +87,16 @@ class ArrayMeshLoader(BaseMeshLoader):
     def GetMeshTextureCoords(self): return self._t
     def GetMeshTriangleFaces(self): return self._f
     def GetMeshModelCenter(self): return self._c
+    def GetOrientBounds(self): return self._obb
+    def GetObjectDimension(self): return self._dim
     def GetTextureMap(self): return self._tex
 
 
 def ConvertPoseMesh2BBox(pose_in_mesh: np.ndarray, loader: BaseMeshLoader) -> np.ndarray:
-    """mesh_loader.hpp:75-81: pose of the (un-centred) mesh frame = pose * translate(-center)."""
+    """mesh_loader.hpp:75-81: T_bbox = T_mesh * translate(-center) * orient_bounds."""
     tf = np.eye(4, dtype=np.float32)
-    tf[:3, 3] = -loader.GetMeshModelCenter()
-    return pose_in_mesh @ tf
+    tf[:3, 3] = -np.asarray(loader.GetMeshModelCenter(), np.float32)
+    return np.asarray(pose_in_mesh, np.float32) @ tf @ np.asarray(loader.GetOrientBounds(), np.float32)
 
 
 def _fptr(a: np.ndarray):

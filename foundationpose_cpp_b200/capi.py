@@ -42,7 +42,7 @@ class ConvDesc(C.Structure):
 class EncoderDesc(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("att", "x0", "w_out", "w1", "w2", "b_out", "b1", "b2", "ln1_g", "ln1_b",
                                           "ln2_g", "ln2_b", "partial", "mean_out")] + \
-               [("n_hyp", C.c_int), ("mode", C.c_int)] + [(n, C.c_void_p) for n in ("dbg_x1", "dbg_h", "dbg_y")]
+               [("n_hyp", C.c_int), ("mode", C.c_int)] + [(n, C.c_void_p) for n in ("dbg_x1", "dbg_h", "dbg_y", "dbg_clocks")]
 
 
 class Mesh(C.Structure):

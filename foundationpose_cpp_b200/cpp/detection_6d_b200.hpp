@@ -3,7 +3,8 @@
 // With Eigen and OpenCV headers present it exposes exactly the reference's types and signatures
 //   detection_6d::Base6DofDetectionModel::{Register,Track}
 //     (detection_6d_foundationpose/include/detection_6d_foundationpose/foundationpose.hpp:16-77)
-//   detection_6d::BaseMeshLoader (mesh_loader.hpp:15-62), ConvertPoseMesh2BBox (:75-81)
+//   detection_6d::BaseMeshLoader (mesh_loader.hpp:15-62: all 12 getters incl. GetOrientBounds / GetObjectDimension,
+//     faces as Vector3ui), ConvertPoseMesh2BBox (:75-81: pose * T(-center) * orient_bounds)
 //   detection_6d::CreateFoundationPoseModelB200(refiner_weights, scorer_weights, mesh_loaders, K, max_h, max_w)
 //     -- the one deliberate difference from CreateFoundationPoseModel (foundationpose.hpp:99-105): two
 //     weight-file paths stand where the reference takes two TensorRT BaseInferCore objects.
@@ -39,6 +40,7 @@ namespace detection_6d {
 using Mat4f = Eigen::Matrix4f;
 using Mat3f = Eigen::Matrix3f;
 using Vec3f = Eigen::Vector3f;
+using Vec3ui = Eigen::Matrix<uint32_t, 3, 1>;
 using Image = cv::Mat;
 inline const uint8_t* image_u8(const Image& m) { return m.ptr<uint8_t>(); }
 inline const float* image_f32(const Image& m) { return m.ptr<float>(); }
@@ -53,7 +55,8 @@ inline float* mat_data(Mat4f& m) { return m.data(); }
 // Stand-ins with the storage conventions of the real types.
 struct Mat4f { float v[16]; const float* data() const { return v; } float* data() { return v; } };  // column-major
 struct Mat3f { float v[9]; float operator()(int r, int c) const { return v[3 * c + r]; } };         // column-major
-struct Vec3f { float v[3]; float operator[](int i) const { return v[i]; } };
+struct Vec3f { float v[3]; float operator[](int i) const { return v[i]; } float& operator[](int i) { return v[i]; } };
+struct Vec3ui { uint32_t v[3]; uint32_t operator[](int i) const { return v[i]; } uint32_t& operator[](int i) { return v[i]; } };
 struct Image {  // continuous row-major pixel buffer
   int rows = 0, cols = 0, channels = 1;
   bool is_float = false;
@@ -74,6 +77,7 @@ inline float* mat_data(Mat4f& m) { return m.data(); }
 class BaseMeshLoader {
  public:
   virtual ~BaseMeshLoader() = default;
+  using Vector3ui = Vec3ui;
   virtual std::string GetName() const noexcept = 0;
   virtual float GetMeshDiameter() const noexcept = 0;
   virtual size_t GetMeshNumVertices() const noexcept = 0;
@@ -81,8 +85,10 @@ class BaseMeshLoader {
   virtual const std::vector<Vec3f>& GetMeshVertices() const noexcept = 0;
   virtual const std::vector<Vec3f>& GetMeshVertexNormals() const noexcept = 0;
   virtual const std::vector<Vec3f>& GetMeshTextureCoords() const noexcept = 0;  // (u, v, unused)
-  virtual const std::vector<std::vector<uint32_t>>& GetMeshTriangleFaces() const noexcept = 0;
+  virtual const std::vector<Vector3ui>& GetMeshTriangleFaces() const noexcept = 0;
   virtual const Vec3f& GetMeshModelCenter() const noexcept = 0;
+  virtual const Mat4f& GetOrientBounds() const noexcept = 0;    // PCA box frame, assimp_mesh_loader.cpp:62-113
+  virtual const Vec3f& GetObjectDimension() const noexcept = 0;  // extents of the vertices along the box axes
   virtual const Image& GetTextureMap() const noexcept = 0;  // RGB u8
 };
 
@@ -197,12 +203,29 @@ inline std::shared_ptr<Base6DofDetectionModel> CreateFoundationPoseModelB200(
   return std::make_shared<FoundationPoseB200>(refiner_weights, scorer_weights, mesh_loaders, K, max_h, max_w);
 }
 
+// mesh_loader.hpp:75-81: T_bbox = T_mesh * T(-center) * orient_bounds
 #ifdef FPB200_HAVE_EIGEN_OPENCV
-// mesh_loader.hpp:75-81
 inline Mat4f ConvertPoseMesh2BBox(const Mat4f& pose_in_mesh, const std::shared_ptr<BaseMeshLoader>& mesh_loader) {
   Mat4f tf_to_center = Mat4f::Identity();
   tf_to_center.block<3, 1>(0, 3) = -mesh_loader->GetMeshModelCenter();
-  return pose_in_mesh * tf_to_center;
+  return pose_in_mesh * tf_to_center * mesh_loader->GetOrientBounds();
+}
+#else
+inline Mat4f ConvertPoseMesh2BBox(const Mat4f& pose_in_mesh, const std::shared_ptr<BaseMeshLoader>& mesh_loader) {
+  auto mul = [](const Mat4f& a, const Mat4f& b) {  // column-major 4x4 product
+    Mat4f c;
+    for (int col = 0; col < 4; ++col)
+      for (int row = 0; row < 4; ++row) {
+        float acc = 0.f;
+        for (int k = 0; k < 4; ++k) acc += a.v[4 * k + row] * b.v[4 * col + k];
+        c.v[4 * col + row] = acc;
+      }
+    return c;
+  };
+  Mat4f tf_to_center{};
+  for (int i = 0; i < 4; ++i) tf_to_center.v[5 * i] = 1.f;
+  for (int c = 0; c < 3; ++c) tf_to_center.v[12 + c] = -mesh_loader->GetMeshModelCenter()[c];
+  return mul(mul(pose_in_mesh, tf_to_center), mesh_loader->GetOrientBounds());
 }
 #endif
 

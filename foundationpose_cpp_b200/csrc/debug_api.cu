@@ -157,6 +157,7 @@ extern "C" int fpb200_debug_encoder_block(const fpb200_encoder_desc* c, int repe
   d.dbg_x1 = static_cast<__half*>(c->dbg_x1);
   d.dbg_h = static_cast<__half*>(c->dbg_h);
   d.dbg_y = static_cast<__half*>(c->dbg_y);
+  d.dbg_clocks = static_cast<unsigned long long*>(c->dbg_clocks);
   EncoderBlockPlan plan;
   if (const char* e = build_encoder_block(d, &plan)) return fail(FPB200_ERR_INVALID, "%s", e);
   return timed_launches([&]() { FPB_CUDA(launch_encoder_block(plan, 0)); }, repeat, ms_out);

@@ -40,6 +40,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "ptx.cuh"
 
@@ -66,8 +67,11 @@ constexpr float kLnEps = 1e-5f;
 template <bool PAIR>
 struct Cfg {
   static constexpr int kCS = PAIR ? 2 : 1;
-  static constexpr int kWStage = kBN * 128 / kCS;  // weight bytes per CTA and (N-tile, k-block)
-  static constexpr int kWRing = PAIR ? 8 : 4;      // 64 KB either way
+  static constexpr int kWTile = kBN * 128 / kCS;   // weight bytes per CTA and (N-tile, k-block)
+  // A ring stage holds TWO k-blocks: the single MMA-issuing thread is close to critical (8 tcgen05.mma of 64
+  // clocks each per hand-shake instead of 4), and the producer issues half as many waits.
+  static constexpr int kWStage = 2 * kWTile;
+  static constexpr int kWRing = PAIR ? 4 : 2;      // 64 KB either way
   // no alignment slack: the dynamic shared-memory window of a kernel without static shared memory starts
   // 1024-byte aligned (checked at kernel entry; SWIZZLE_128B tiles need it)
   static constexpr size_t kSmem = kABytes + kSlabBytes + kWRing * kWStage + kBarBytes;
@@ -100,7 +104,12 @@ __device__ __forceinline__ void umma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tme
       : "memory");
 }
 
-template <bool PAIR>
+template <int V>
+using ic = std::integral_constant<int, V>;
+
+// TIMED: a second instantiation with phase clocks (tools/bench_encoder.py); the product kernel carries none of it
+// (even disabled at run time the extra branches in the MMA-issuing thread cost 30 %).
+template <bool PAIR, bool TIMED>
 __global__ void __launch_bounds__(kThreads, 1)
 encoder_block_kernel(const __grid_constant__ EncoderBlockParams p) {
   using C = Cfg<PAIR>;
@@ -199,7 +208,7 @@ encoder_block_kernel(const __grid_constant__ EncoderBlockParams p) {
       __syncwarp();
       for (int g = 0; g < 3; ++g) {
         for (int nt = 0; nt < kNT; ++nt) {
-          for (int kb = 0; kb < kKB; ++kb) {
+          for (int kb = 0; kb < kKB; kb += 2) {
             ptx::mbar_wait(wempty(ws), wph ^ 1u);
             if (ptx::elect_one()) {
               const uint32_t bar = on_leader(wfull(ws));
@@ -208,9 +217,11 @@ encoder_block_kernel(const __grid_constant__ EncoderBlockParams p) {
               if (PAIR) {
                 ptx::mbar_expect_tx_cluster(bar, C::kWStage);
                 ptx::tma_load_2d_pair(dst, &p.tm_w[g], bar, kb * 64, nrow);
+                ptx::tma_load_2d_pair(dst + C::kWTile, &p.tm_w[g], bar, kb * 64 + 64, nrow);
               } else {
                 ptx::mbar_expect_tx(bar, C::kWStage);
                 ptx::tma_load_2d(dst, &p.tm_w[g], bar, kb * 64, nrow);
+                ptx::tma_load_2d(dst + C::kWTile, &p.tm_w[g], bar, kb * 64 + 64, nrow);
               }
             }
             __syncwarp();
@@ -245,6 +256,18 @@ encoder_block_kernel(const __grid_constant__ EncoderBlockParams p) {
       int ws = 0;
       uint32_t wph = 0;
       int it = 0;
+      // optional phase clocks (tools/bench_encoder.py): where the issuing thread of CTA 0 waits
+      const bool timed = TIMED && p.dbg_clocks != nullptr && blockIdx.x == 0 && lane == 0;
+      long long mk[6] = {0, 0, 0, 0, 0, 0};
+      long long m_prev = timed ? clock64() : 0;
+      auto mtick = [&](int k) {
+        if constexpr (!TIMED) return;
+        if (timed) {
+          const long long now = clock64();
+          mk[k] += now - m_prev;
+          m_prev = now;
+        }
+      };
       for (int item = cluster_id; item < n_items; item += num_clusters, ++it) {
         const uint32_t bpar = it & 1;  // parity of the once-per-block barriers
         for (int g = 0; g < 3; ++g) {
@@ -252,36 +275,47 @@ encoder_block_kernel(const __grid_constant__ EncoderBlockParams p) {
             const int t = g * kNT + nt;              // accumulator tile of the block (0..11)
             const int acc = t & 1;
             const int use = it * 6 + (t >> 1);       // how often this stage has been used before
+            mtick(5);
             ptx::mbar_wait(accempty(acc), (use & 1) ^ 1u);
             ptx::tc_fence_after();
+            mtick(0);
             const uint32_t d_tmem = tmem_base + acc * kBN;
-            for (int kb = 0; kb < kKB; ++kb) {
-              if (nt == 0) {  // first use of the A k-block by this GEMM
+            for (int kb = 0; kb < kKB; kb += 2) {
+              if (nt == 0) {  // first use of these two A k-blocks by this GEMM
+                mtick(5);
                 ptx::mbar_wait(g == 0 ? afull(kb) : (g == 1 ? xready(kb) : hready(kb)), bpar);
+                ptx::mbar_wait(g == 0 ? afull(kb + 1) : (g == 1 ? xready(kb + 1) : hready(kb + 1)), bpar);
+                mtick(1 + g);
               }
+              mtick(5);
               ptx::mbar_wait(wfull(ws), wph);
               ptx::tc_fence_after();
+              mtick(4);
               if (ptx::elect_one()) {
                 const uint64_t bdesc = desc(w_lo0 + ws * (C::kWStage >> 4));
                 if (g < 2) {
                   const uint64_t adesc = desc(a_lo0 + kb * (kTileA >> 4));
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    if (PAIR) ptx::umma_f16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)(kb | k));
-                    else ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)(kb | k));
+                  for (int k = 0; k < 8; ++k) {
+                    // k-block (k >> 2): next A tile (kTileA bytes on) / next weight tile of the stage
+                    const uint64_t ad = adesc + (uint64_t)((k >> 2) * (kTileA >> 4)) + 2u * (k & 3);
+                    const uint64_t bd = bdesc + (uint64_t)((k >> 2) * (C::kWTile >> 4)) + 2u * (k & 3);
+                    if (PAIR) ptx::umma_f16_pair(d_tmem, ad, bd, idesc, (uint32_t)(kb | k));
+                    else ptx::umma_f16(d_tmem, ad, bd, idesc, (uint32_t)(kb | k));
                   }
                 } else {
                   // A = h from tensor memory: 16 K values = 8 packed columns per MMA
                   const uint32_t a_tmem = tmem_base + kColR + kb * 32;
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    if (PAIR) umma_f16_ts_pair(d_tmem, a_tmem + 8u * k, bdesc + 2u * k, idesc, (uint32_t)(kb | k));
-                    else ptx::umma_f16_ts(d_tmem, a_tmem + 8u * k, bdesc + 2u * k, idesc, (uint32_t)(kb | k));
+                  for (int k = 0; k < 8; ++k) {
+                    const uint64_t bd = bdesc + (uint64_t)((k >> 2) * (C::kWTile >> 4)) + 2u * (k & 3);
+                    if (PAIR) umma_f16_ts_pair(d_tmem, a_tmem + 8u * k, bd, idesc, (uint32_t)(kb | k));
+                    else ptx::umma_f16_ts(d_tmem, a_tmem + 8u * k, bd, idesc, (uint32_t)(kb | k));
                   }
                 }
                 if (PAIR) ptx::umma_commit_pair_mcast(wempty(ws), kAllCtas);
                 else ptx::umma_commit(wempty(ws));
-                if (kb == kKB - 1) {
+                if (kb == kKB - 2) {
                   if (PAIR) ptx::umma_commit_pair_mcast(accfull(acc), kAllCtas);
                   else ptx::umma_commit(accfull(acc));
                 }
@@ -295,209 +329,253 @@ encoder_block_kernel(const __grid_constant__ EncoderBlockParams p) {
           }
         }
       }
+      if (timed) {
+        mtick(5);
+        for (int k = 0; k < 6; ++k) p.dbg_clocks[k] = (unsigned long long)mk[k];
+        p.dbg_clocks[6] = (unsigned long long)it;
+      }
     }
   } else {
     // ================================ epilogue ================================
-    const int ew = warp - 2;
+    // Everything below is instantiated twice, once per 64-column half (SIDX) a warp set owns; the tile / k-block
+    // loops stay rolled (fully unrolled the kernel is 290 KB of SASS and thrashes the instruction cache: measured
+    // 285 us against 208 us) but their counters are warp-uniform, so with SIDX a compile-time constant every column
+    // offset is uniform and the bias / LayerNorm vectors in the kernel parameters are fetched with uniform
+    // constant loads (LDCU.128: four values per instruction into uniform registers that the FADD / FFMA read
+    // directly).  Per-thread indexed LDC loads were 47 % of the warp stalls; global loads before that were worse.
+    auto run_epilogue = [&](auto sidx_tag) {
+    constexpr int sidx = decltype(sidx_tag)::value;  // which 64-column half of every 128-column tile this warp owns
     const int q = warp & 3;      // TMEM lane quarter this warp may access
-    const int sidx = ew >> 2;    // which 64-column half of every 128-column tile (= k-block parity) this warp owns
     const int row = q * 32 + lane;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float* red = reinterpret_cast<float*>(smem_raw + (red_base - ptx::smem_u32(smem_raw)));  // [2][128] sum, [2][128] sumsq
     // byte offset of 16-byte chunk c of this thread's row inside a SW128 tile
     auto chunk_off = [&](int c) { return static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4)); };
     int it = 0;
-    for (int item = cluster_id; item < n_items; item += num_clusters, ++it) {
-      const long long row_g = static_cast<long long>(item * CS + crank) * kBM + row;  // this thread's token row
-      float mean = 0.f, rstd = 0.f;
-      for (int g = 0; g < 3; ++g) {
-        float s1 = 0.f, s2 = 0.f;  // row statistics of the fp16-rounded pre-LayerNorm sum (GEMM 1 and 3)
-        const float* bias_g = g == 0 ? p.b_out : (g == 1 ? p.b1 : p.b2);
-        for (int nt = 0; nt < kNT; ++nt) {
-          const int t = g * kNT + nt;
-          const int acc = t & 1;
-          const int use = it * 6 + (t >> 1);
-          const int kb = 2 * nt + sidx;   // the k-block (64 columns) this warp produces
-          const int c0 = kb * 64;         // its first column
-          // ---- residual of this thread's row, fetched before the accumulator is waited for
-          uint32_t res[32];
-          if (g == 0) {
-            ptx::mbar_wait(sfull, (it * kNT + nt) & 1);
+    long long row_g = 0;
+    float s1 = 0.f, s2 = 0.f;  // row statistics of the pre-LayerNorm sum (GEMM 1 and 3)
+    const bool timed = TIMED && p.dbg_clocks != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+    long long tk[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = timed ? clock64() : 0;
+    auto tick = [&](int k) {
+      if constexpr (!TIMED) return;
+      if (timed) {
+        const long long now = clock64();
+        tk[k] += now - t_prev;
+        t_prev = now;
+      }
+    };
+
+    // ---- pass A of one accumulator tile; the GEMM index is a compile-time constant so that the residual / ReLU
+    // variants carry no predicated-off instructions.  Bias / LayerNorm vectors come from the constant bank
+    // (kernel parameters): a warp-uniform LDC instead of a global load + descriptor set-up per pair.
+    auto pass_a = [&](auto g_tag, int nt) {
+      constexpr int G = decltype(g_tag)::value;
+      const float* bias_g = G == 0 ? p.vec.b_out : (G == 1 ? p.vec.b1 : p.vec.b2);
+      const int t = G * kNT + nt;
+      const int acc = t & 1;
+      const int use = it * 6 + (t >> 1);
+      const int kb = 2 * nt + sidx;   // the k-block (64 columns) this warp produces
+      const int c0 = kb * 64;         // its first column
+      // residual of this thread's row, fetched before the accumulator is waited for
+      uint32_t res[32];
+      if constexpr (G == 0) {
+        ptx::mbar_wait(sfull, (it * kNT + nt) & 1);
+        tick(0);  // waiting for the residual slab
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              ld_shared_v4u(slab_base + sidx * kTileA + chunk_off(c), res[4 * c], res[4 * c + 1], res[4 * c + 2], res[4 * c + 3]);
-          } else if (g == 2) {
+        for (int c = 0; c < 8; ++c)
+          ld_shared_v4u(slab_base + sidx * kTileA + chunk_off(c), res[4 * c], res[4 * c + 1], res[4 * c + 2], res[4 * c + 3]);
+      } else if constexpr (G == 2) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              ld_shared_v4u(a_base + kb * kTileA + chunk_off(c), res[4 * c], res[4 * c + 1], res[4 * c + 2], res[4 * c + 3]);
+        for (int c = 0; c < 8; ++c)
+          ld_shared_v4u(a_base + kb * kTileA + chunk_off(c), res[4 * c], res[4 * c + 1], res[4 * c + 2], res[4 * c + 3]);
+      }
+      ptx::mbar_wait(accfull(acc), use & 1);
+      ptx::tc_fence_after();
+      tick(1 + G);  // waiting for the accumulator of GEMM G
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld_32x32b_x32(tlane + acc * kBN + sidx * 64, r0);
+      ptx::tmem_ld_32x32b_x32(tlane + acc * kBN + sidx * 64 + 32, r1);
+      ptx::tmem_ld_wait();
+      // the accumulator stage is free again as soon as it sits in registers
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa_rank(accempty(acc), 0));
+        else ptx::mbar_arrive(accempty(acc));
+      }
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v0 = __uint_as_float(j < 16 ? r0[2 * j] : r1[2 * j - 32]) + bias_g[c0 + 2 * j];
+        float v1 = __uint_as_float(j < 16 ? r0[2 * j + 1] : r1[2 * j - 31]) + bias_g[c0 + 2 * j + 1];
+        if constexpr (G != 1) {
+          const float2 rr = unpack_half2(res[j]);
+          v0 += rr.x;
+          v1 += rr.y;
+          s1 += v0 + v1;
+          s2 = fmaf(v0, v0, fmaf(v1, v1, s2));
+        } else {
+          v0 = fmaxf(v0, 0.f);
+          v1 = fmaxf(v1, 0.f);
+        }
+        pk[j] = pack_half2(v0, v1);
+      }
+      if constexpr (G == 0) {  // the slab has been consumed (its values went into pk[])
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(sempty);
+      }
+      if constexpr (G < 2) {
+        // GEMM 1: pre-LayerNorm sum, GEMM 2: h -> R (packed fp16: K pair per column)
+        uint32_t a16[16], b16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          a16[j] = pk[j];
+          b16[j] = pk[16 + j];
+        }
+        ptx::tmem_st_32x32b_x16(tlane + kColR + kb * 32, a16);
+        ptx::tmem_st_32x32b_x16(tlane + kColR + kb * 32 + 16, b16);
+        ptx::tmem_st_wait();
+        if constexpr (G == 1) {
+          if (p.dbg_h && row_g < p.rows) {
+            uint4* dst = reinterpret_cast<uint4*>(p.dbg_h + row_g * kD + c0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
           }
-          ptx::mbar_wait(accfull(acc), use & 1);
-          ptx::tc_fence_after();
-          uint32_t r0[32], r1[32];
-          ptx::tmem_ld_32x32b_x32(tlane + acc * kBN + sidx * 64, r0);
-          ptx::tmem_ld_32x32b_x32(tlane + acc * kBN + sidx * 64 + 32, r1);
-          ptx::tmem_ld_wait();
-          // the accumulator stage is free again as soon as it sits in registers
+          // publish h k-block kb to the MMA warp (A operand of GEMM 3 in tensor memory)
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa_rank(accempty(acc), 0));
-            else ptx::mbar_arrive(accempty(acc));
-          }
-          uint32_t pk[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_g + c0) + j);
-            float v0 = __uint_as_float(j < 16 ? r0[2 * j] : r1[2 * j - 32]) + bb.x;
-            float v1 = __uint_as_float(j < 16 ? r0[2 * j + 1] : r1[2 * j - 31]) + bb.y;
-            if (g != 1) {
-              const float2 rr = unpack_half2(res[j]);
-              v0 += rr.x;
-              v1 += rr.y;
-            } else {
-              v0 = fmaxf(v0, 0.f);
-              v1 = fmaxf(v1, 0.f);
-            }
-            pk[j] = pack_half2(v0, v1);
-            if (g != 1) {
-              const float2 vr = unpack_half2(pk[j]);  // statistics of what LayerNorm will read
-              s1 += vr.x + vr.y;
-              s2 = fmaf(vr.x, vr.x, fmaf(vr.y, vr.y, s2));
-            }
-          }
-          if (g == 0) {  // the slab has been consumed (its values went into pk[])
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(sempty);
-          }
-          if (g < 2) {
-            // GEMM 1: pre-LayerNorm sum, GEMM 2: h -> R (packed fp16: K pair per column)
-            uint32_t a16[16], b16[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              a16[j] = pk[j];
-              b16[j] = pk[16 + j];
-            }
-            ptx::tmem_st_32x32b_x16(tlane + kColR + kb * 32, a16);
-            ptx::tmem_st_32x32b_x16(tlane + kColR + kb * 32 + 16, b16);
-            ptx::tmem_st_wait();
-            if (g == 1) {
-              if (p.dbg_h && row_g < p.rows) {
-                uint4* dst = reinterpret_cast<uint4*>(p.dbg_h + row_g * kD + c0);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) dst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-              }
-              // publish h k-block kb to the MMA warp (A operand of GEMM 3 in tensor memory)
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa_rank(hready(kb), 0));
-                else ptx::mbar_arrive(hready(kb));
-              }
-            }
-          } else {
-            // GEMM 3: pre-LayerNorm sum written in place over x1 (this thread's own row of its own k-block)
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              ptx::st_shared_v4(a_base + kb * kTileA + chunk_off(c), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa_rank(hready(kb), 0));
+            else ptx::mbar_arrive(hready(kb));
           }
         }
-        if (g == 1) continue;
-        // ---- row statistics: combine the two column halves
-        red[sidx * kBM + row] = s1;
-        red[(2 + sidx) * kBM + row] = s2;
-        named_barrier_sync(1, 32 * kEpiWarps);
-        s1 += red[(sidx ^ 1) * kBM + row];
-        s2 += red[(2 + (sidx ^ 1)) * kBM + row];
-        named_barrier_sync(1, 32 * kEpiWarps);  // red[] may be rewritten
-        mean = s1 * (1.f / kD);
-        rstd = rsqrtf(fmaxf(s2 * (1.f / kD) - mean * mean, 0.f) + kLnEps);
-        const float* gam = g == 0 ? p.ln1_g : p.ln2_g;
-        const float* bet = g == 0 ? p.ln1_b : p.ln2_b;
-        if (g == 0) {
-          // ---- LayerNorm 1: R -> x1 (fp16) into the A buffer, k-block by k-block; GEMM 2 follows right behind
-          for (int j = 0; j < 4; ++j) {
-            const int kb = 2 * j + sidx, c0 = kb * 64;
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(tlane + kColR + kb * 32, r);
-            ptx::tmem_ld_wait();
-            uint32_t pk[32];
+      } else {
+        // GEMM 3: pre-LayerNorm sum written in place over x1 (this thread's own row of its own k-block)
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float2 v = unpack_half2(r[e]);
-              const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + c0) + e);
-              const float2 bb = __ldg(reinterpret_cast<const float2*>(bet + c0) + e);
-              pk[e] = pack_half2((v.x - mean) * rstd * gg.x + bb.x, (v.y - mean) * rstd * gg.y + bb.y);
-            }
+        for (int c = 0; c < 8; ++c)
+          ptx::st_shared_v4(a_base + kb * kTileA + chunk_off(c), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
+      tick(4 + G);  // pass A of GEMM G
+    };
+    // ---- row statistics of a 512-wide row: combine the two column halves -> (scale, shift) of the normalisation
+    auto row_affine = [&](float& a, float& b) {
+      red[sidx * kBM + row] = s1;
+      red[(2 + sidx) * kBM + row] = s2;
+      named_barrier_sync(1, 32 * kEpiWarps);
+      const float t1 = s1 + red[(sidx ^ 1) * kBM + row];
+      const float t2 = s2 + red[(2 + (sidx ^ 1)) * kBM + row];
+      named_barrier_sync(1, 32 * kEpiWarps);  // red[] may be rewritten
+      const float mean = t1 * (1.f / kD);
+      a = rsqrtf(fmaxf(t2 * (1.f / kD) - mean * mean, 0.f) + kLnEps);
+      b = -mean * a;  // (v - mean) * rstd = v * a + b
+      s1 = s2 = 0.f;
+      tick(7);  // statistics exchange
+    };
+
+    for (int item = cluster_id; item < n_items; item += num_clusters, ++it) {
+      row_g = static_cast<long long>(item * CS + crank) * kBM + row;  // this thread's token row
+      float na, nb;
+      // ================= GEMM 1: out-projection + residual, then LayerNorm 1 -> x1 in the A buffer
+#pragma unroll 1
+      for (int nt = 0; nt < kNT; ++nt) pass_a(ic<0>{}, nt);
+      row_affine(na, nb);
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int kb = 2 * j + sidx, c0 = kb * 64;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tlane + kColR + kb * 32, r);
+        ptx::tmem_ld_wait();
+        uint32_t pk[32];
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              ptx::st_shared_v4(a_base + kb * kTileA + chunk_off(c), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            if (p.dbg_x1 && row_g < p.rows) {
-              uint4* dst = reinterpret_cast<uint4*>(p.dbg_x1 + row_g * kD + c0);
+        for (int e = 0; e < 32; ++e) {
+          const float2 v = unpack_half2(r[e]);
+          pk[e] = pack_half2(fmaf(fmaf(v.x, na, nb), p.vec.ln1_g[c0 + 2 * e], p.vec.ln1_b[c0 + 2 * e]),
+                             fmaf(fmaf(v.y, na, nb), p.vec.ln1_g[c0 + 2 * e + 1], p.vec.ln1_b[c0 + 2 * e + 1]));
+        }
 #pragma unroll
-              for (int c = 0; c < 8; ++c) dst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            }
-            ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's operand reads
-            ptx::tc_fence_before();    // the R columns just read will be overwritten by GEMM 2's pass A
-            __syncwarp();
-            if (lane == 0) {
-              if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa_rank(xready(kb), 0));
-              else ptx::mbar_arrive(xready(kb));
-            }
-          }
-        } else {
-          // ---- LayerNorm 2 + partial token sums: groups of 16 consecutive rows (= half a warp)
-          const int hl = lane & 15;
-          const long long grp = row_g >> 4;  // global group index of this thread's row
-          const bool grp_ok = (row_g - hl + kGroup) <= p.rows;  // rows is a multiple of 16
-          for (int j = 0; j < 4; ++j) {
-            const int kb = 2 * j + sidx, c0 = kb * 64;
-            uint32_t r[32];
+        for (int c = 0; c < 8; ++c)
+          ptx::st_shared_v4(a_base + kb * kTileA + chunk_off(c), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        if (p.dbg_x1 && row_g < p.rows) {
+          uint4* dst = reinterpret_cast<uint4*>(p.dbg_x1 + row_g * kD + c0);
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              ld_shared_v4u(a_base + kb * kTileA + chunk_off(c), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-            float y[64];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float2 v = unpack_half2(r[e]);
-              const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + c0) + e);
-              const float2 bb = __ldg(reinterpret_cast<const float2*>(bet + c0) + e);
-              y[2 * e] = (v.x - mean) * rstd * gg.x + bb.x;
-              y[2 * e + 1] = (v.y - mean) * rstd * gg.y + bb.y;
-            }
-            if (p.dbg_y && row_g < p.rows) {
-              uint4* dst = reinterpret_cast<uint4*>(p.dbg_y + row_g * kD + c0);
-#pragma unroll
-              for (int c = 0; c < 8; ++c)
-                dst[c] = make_uint4(pack_half2(y[8 * c], y[8 * c + 1]), pack_half2(y[8 * c + 2], y[8 * c + 3]),
-                                    pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7]));
-            }
-            // recursive halving over the 16 lanes of the group: after the level with lane bit b, a lane keeps the
-            // half of its columns selected by that bit, summed with its partner's copy (fixed tree, deterministic)
-#pragma unroll
-            for (int lvl = 0; lvl < 4; ++lvl) {
-              const int bit = 8 >> lvl;           // lane bit of this level
-              const int half = 32 >> lvl;         // columns kept
-              const bool up = (lane & bit) != 0;
-#pragma unroll
-              for (int e = 0; e < half; ++e) {
-                const float keep = up ? y[e + half] : y[e];
-                const float send = up ? y[e] : y[e + half];
-                y[e] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-              }
-            }
-            // this lane now holds the group sums of columns c0 + 4 * hl' .. + 4, hl' = bit-reversed... see below
-            if (grp_ok) {
-              // kept half at level 0 is [32 b3, +32), at level 1 [16 b2, +16) inside it, ...: first column = 32 b3 + 16 b2 + 8 b1 + 4 b0
-              const int col = ((hl & 8) ? 32 : 0) + ((hl & 4) ? 16 : 0) + ((hl & 2) ? 8 : 0) + ((hl & 1) ? 4 : 0);
-              *reinterpret_cast<float4*>(p.partial + grp * kD + c0 + col) = make_float4(y[0], y[1], y[2], y[3]);
-            }
-          }
-          // the A buffer may be refilled with the next block's attention rows
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(afree);
+          for (int c = 0; c < 8; ++c) dst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's operand reads
+        ptx::tc_fence_before();    // the R columns just read will be overwritten by GEMM 2's pass A
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa_rank(xready(kb), 0));
+          else ptx::mbar_arrive(xready(kb));
         }
       }
+      tick(8);  // LayerNorm 1 pass
+      // ================= GEMM 2: FFN first layer + ReLU -> h in tensor memory
+#pragma unroll 1
+      for (int nt = 0; nt < kNT; ++nt) pass_a(ic<1>{}, nt);
+      // ================= GEMM 3: FFN second layer + residual, then LayerNorm 2 + partial token sums
+#pragma unroll 1
+      for (int nt = 0; nt < kNT; ++nt) pass_a(ic<2>{}, nt);
+      row_affine(na, nb);
+      {
+        // groups of 16 consecutive rows (= half a warp)
+        const int hl = lane & 15;
+        const long long grp = row_g >> 4;  // global group index of this thread's row
+        const bool grp_ok = (row_g - hl + kGroup) <= p.rows;  // rows is a multiple of 16
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int kb = 2 * j + sidx, c0 = kb * 64;
+          uint32_t r[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            ld_shared_v4u(a_base + kb * kTileA + chunk_off(c), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+          float y[64];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float2 v = unpack_half2(r[e]);
+            y[2 * e] = fmaf(fmaf(v.x, na, nb), p.vec.ln2_g[c0 + 2 * e], p.vec.ln2_b[c0 + 2 * e]);
+            y[2 * e + 1] = fmaf(fmaf(v.y, na, nb), p.vec.ln2_g[c0 + 2 * e + 1], p.vec.ln2_b[c0 + 2 * e + 1]);
+          }
+          if (p.dbg_y && row_g < p.rows) {
+            uint4* dst = reinterpret_cast<uint4*>(p.dbg_y + row_g * kD + c0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              dst[c] = make_uint4(pack_half2(y[8 * c], y[8 * c + 1]), pack_half2(y[8 * c + 2], y[8 * c + 3]),
+                                  pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7]));
+          }
+          // recursive halving over the 16 lanes of the group: at the level of lane bit b a lane keeps the half of
+          // its columns selected by that bit, summed with its partner's copy (fixed tree: deterministic)
+#pragma unroll
+          for (int lvl = 0; lvl < 4; ++lvl) {
+            const int bit = 8 >> lvl;           // lane bit of this level
+            const int half = 32 >> lvl;         // columns kept
+            const bool up = (lane & bit) != 0;
+#pragma unroll
+            for (int e = 0; e < half; ++e) {
+              const float keep = up ? y[e + half] : y[e];
+              const float send = up ? y[e] : y[e + half];
+              y[e] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+          }
+          if (grp_ok) {
+            // kept half at level 0 is [32 b3, +32), at level 1 [16 b2, +16) inside it, ...: first column = 32 b3 + 16 b2 + 8 b1 + 4 b0
+            const int col = ((hl & 8) ? 32 : 0) + ((hl & 4) ? 16 : 0) + ((hl & 2) ? 8 : 0) + ((hl & 1) ? 4 : 0);
+            *reinterpret_cast<float4*>(p.partial + grp * kD + c0 + col) = make_float4(y[0], y[1], y[2], y[3]);
+          }
+        }
+        // the A buffer may be refilled with the next block's attention rows
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(afree);
+        tick(9);  // LayerNorm 2 pass + partial sums
+      }
     }
+    if (timed) {
+      for (int k = 0; k < 12; ++k) p.dbg_clocks[8 + k] = (unsigned long long)tk[k];
+      p.dbg_clocks[20] = (unsigned long long)it;
+    }
+    };  // run_epilogue
+    if (((warp - 2) >> 2) == 0) run_epilogue(ic<0>{});
+    else run_epilogue(ic<1>{});
   }
 
   ptx::tc_fence_before();
@@ -561,10 +639,15 @@ const char* encoder_block_init() {
       return "cuTensorMapEncodeTiled not available from the CUDA driver";
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  if (cudaFuncSetAttribute(encoder_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)Cfg<false>::kSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(encoder_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)Cfg<true>::kSmem) != cudaSuccess)
+  cudaError_t e = cudaSuccess;
+  auto set_attr = [&](auto kernel, size_t smem) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  };
+  set_attr(encoder_block_kernel<false, false>, Cfg<false>::kSmem);
+  set_attr(encoder_block_kernel<true, false>, Cfg<true>::kSmem);
+  set_attr(encoder_block_kernel<false, true>, Cfg<false>::kSmem);
+  set_attr(encoder_block_kernel<true, true>, Cfg<true>::kSmem);
+  if (e != cudaSuccess)
     return "cudaFuncSetAttribute(encoder_block smem) failed (not an sm_100a device?)";
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (dev < 64) inited |= 1ull << dev;
@@ -587,11 +670,22 @@ const char* build_encoder_block(const EncoderBlockDesc& d, EncoderBlockPlan* pla
   const __half* w[3] = {d.w_out, d.w1, d.w2};
   for (int g = 0; g < 3; ++g)
     if (const char* e = encode_2d(&p.tm_w[g], w[g], kD, kD, 64, kBN / cs, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return e;
-  p.b_out = d.b_out; p.b1 = d.b1; p.b2 = d.b2;
-  p.ln1_g = d.ln1_g; p.ln1_b = d.ln1_b; p.ln2_g = d.ln2_g; p.ln2_b = d.ln2_b;
+  {
+    // bias / LayerNorm vectors travel BY VALUE in the kernel parameters (constant bank): 14 KB copied once per plan
+    const float* src[7] = {d.b_out, d.b1, d.b2, d.ln1_g, d.ln1_b, d.ln2_g, d.ln2_b};
+    float* dst[7] = {p.vec.b_out, p.vec.b1, p.vec.b2, p.vec.ln1_g, p.vec.ln1_b, p.vec.ln2_g, p.vec.ln2_b};
+    for (int i = 0; i < 7; ++i) {
+      if (!src[i]) return "encoder_block: null bias / LayerNorm vector";
+      if (d.vectors_on_host)
+        memcpy(dst[i], src[i], sizeof(float) * kD);
+      else if (cudaMemcpy(dst[i], src[i], sizeof(float) * kD, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return "encoder_block: reading the bias / LayerNorm vectors failed";
+    }
+  }
   p.partial = d.partial;
   p.rows = (int)rows;
   p.dbg_x1 = d.dbg_x1; p.dbg_h = d.dbg_h; p.dbg_y = d.dbg_y;
+  p.dbg_clocks = d.dbg_clocks;
   plan->pair = pair;
   const int items = (n_blocks + cs - 1) / cs;
   const int cap = g_num_sms / cs;
@@ -616,8 +710,13 @@ cudaError_t launch_encoder_block(const EncoderBlockPlan& plan, cudaStream_t stre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = plan.pair ? cudaLaunchKernelEx(&cfg, encoder_block_kernel<true>, plan.p)
-                            : cudaLaunchKernelEx(&cfg, encoder_block_kernel<false>, plan.p);
+  cudaError_t e;
+  if (plan.p.dbg_clocks)
+    e = plan.pair ? cudaLaunchKernelEx(&cfg, encoder_block_kernel<true, true>, plan.p)
+                  : cudaLaunchKernelEx(&cfg, encoder_block_kernel<false, true>, plan.p);
+  else
+    e = plan.pair ? cudaLaunchKernelEx(&cfg, encoder_block_kernel<true, false>, plan.p)
+                  : cudaLaunchKernelEx(&cfg, encoder_block_kernel<false, false>, plan.p);
   if (e != cudaSuccess) return e;
   const int n4 = plan.n_hyp * (kD / 4);
   encoder_mean_kernel<<<(n4 + 255) / 256, 256, 0, stream>>>(plan.p.partial, plan.mean_out, plan.n_hyp);

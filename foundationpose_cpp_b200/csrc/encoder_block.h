@@ -10,15 +10,21 @@
 
 namespace fpb {
 
+// Bias / LayerNorm vectors of the layer, passed by value inside the kernel parameters: the epilogue threads all read
+// the same element at the same time, which the constant bank serves as one broadcast (LDC) without a global load.
+struct EncoderVectors {
+  float b_out[512], b1[512], b2[512], ln1_g[512], ln1_b[512], ln2_g[512], ln2_b[512];
+};
+
 struct EncoderBlockParams {
   CUtensorMap tm_att;   // attention output [rows, 512] fp16, box (64, 128)
   CUtensorMap tm_x0;    // layer input (residual of the out-projection) [rows, 512] fp16, box (64, 128)
   CUtensorMap tm_w[3];  // Wout, W1, W2: [512 out][512 in] fp16 K-major, box (64, 128 or 64)
-  const float *b_out, *b1, *b2;
-  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  EncoderVectors vec;
   float* partial;       // [rows / 16][512] f32: sums of LayerNorm2 outputs over groups of 16 consecutive tokens
   int rows;             // hypotheses * 400 (a multiple of 16)
   __half *dbg_x1, *dbg_h, *dbg_y;  // tests: LayerNorm1 output, FFN activation, LayerNorm2 output [rows, 512]; or null
+  unsigned long long* dbg_clocks;  // optional [24]: phase clock sums of CTA 0 (MMA issuer [0,8), one epilogue thread [8,24))
 };
 
 struct EncoderBlockDesc {
@@ -32,6 +38,8 @@ struct EncoderBlockDesc {
   int n_hyp = 0;
   int mode = 0;               // 0 automatic, 1 single CTAs, 2 CTA pairs (tcgen05.mma.cta_group::2)
   __half *dbg_x1 = nullptr, *dbg_h = nullptr, *dbg_y = nullptr;
+  unsigned long long* dbg_clocks = nullptr;
+  bool vectors_on_host = false;  // b_* / ln* point to host memory (plan building then never touches the device)
 };
 
 struct EncoderBlockPlan {

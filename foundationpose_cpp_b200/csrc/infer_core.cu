@@ -80,6 +80,37 @@ int fpb200_infer_create(const char* weights, int kind, int max_batch, int device
   });
 }
 
+// Device buffers for callers that hold blobs but do not link the CUDA runtime themselves (the B200InferCore plugin
+// of cpp/b200_infer_core.hpp is compiled with the host compiler only).
+int fpb200_device_alloc(size_t bytes, int device, void** out) {
+  return guarded([&]() -> int {
+    FPB_REQUIRE(out, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      throw CudaError("no CUDA device available: this library has no CPU fallback");
+    FPB_CUDA(cudaSetDevice(device));
+    FPB_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    FPB_CUDA(cudaMemset(*out, 0, bytes));
+    return FPB200_OK;
+  });
+}
+
+void fpb200_device_free(void* ptr) {
+  if (ptr) cudaFree(ptr);
+}
+
+int fpb200_memcpy(void* dst, const void* src, size_t bytes, int kind) {
+  return guarded([&]() -> int {
+    FPB_REQUIRE(dst && src, "null argument");
+    const cudaMemcpyKind k = kind == FPB200_COPY_H2D ? cudaMemcpyHostToDevice
+                             : kind == FPB200_COPY_D2H ? cudaMemcpyDeviceToHost
+                                                       : cudaMemcpyDeviceToDevice;
+    FPB_REQUIRE(kind >= FPB200_COPY_H2D && kind <= FPB200_COPY_D2D, "bad copy kind %d", kind);
+    FPB_CUDA(cudaMemcpy(dst, src, bytes, k));
+    return FPB200_OK;
+  });
+}
+
 void fpb200_infer_destroy(fpb200_infer_core* c) {
   if (!c) return;
   cudaStreamSynchronize(c->stream);

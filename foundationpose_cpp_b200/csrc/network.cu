@@ -53,6 +53,7 @@ WeightFile::WeightFile(const std::string& path, int expected_kind) : path_(path)
     for (int d = 0; d < 4; ++d) t.dims[d] = (int)e.dims[d];
     tensors_[std::string(e.name, strnlen(e.name, sizeof(e.name)))] = t;
   }
+  host_ = std::move(buf);
 }
 
 WeightFile::~WeightFile() {
@@ -227,10 +228,15 @@ void Network::add_encoder_layer(Plan& p, int n, const std::string& h, float* mea
     // each 128-token row block on chip through the three GEMMs (encoder_block.cu)
     EncoderBlockDesc d;
     d.att = A.att; d.x0 = A.d0; d.n_hyp = n;
-    d.w_out = W.f16(h + ".out.w", 512, 512); d.b_out = W.f32(h + ".out.b", 512);
-    d.w1 = W.f16(h + ".ff1.w", 512, 512); d.b1 = W.f32(h + ".ff1.b", 512);
-    d.w2 = W.f16(h + ".ff2.w", 512, 512); d.b2 = W.f32(h + ".ff2.b", 512);
-    d.ln1_g = g1; d.ln1_b = b1; d.ln2_g = g2; d.ln2_b = b2;
+    d.w_out = W.f16(h + ".out.w", 512, 512);
+    d.w1 = W.f16(h + ".ff1.w", 512, 512);
+    d.w2 = W.f16(h + ".ff2.w", 512, 512);
+    // the fused kernel takes the vectors by value: read them from the host copy of the file, so that building a plan
+    // never synchronises with the device (a peer session of the same process may be spinning on it)
+    d.b_out = W.host_f32(h + ".out.b", 512); d.b1 = W.host_f32(h + ".ff1.b", 512); d.b2 = W.host_f32(h + ".ff2.b", 512);
+    d.ln1_g = W.host_f32(h + ".ln1.g", 512); d.ln1_b = W.host_f32(h + ".ln1.b", 512);
+    d.ln2_g = W.host_f32(h + ".ln2.g", 512); d.ln2_b = W.host_f32(h + ".ln2.b", 512);
+    d.vectors_on_host = true;
     d.partial = A.mean_part; d.mean_out = mean_out;
     EncoderBlockPlan ep;
     if (const char* e = build_encoder_block(d, &ep)) throw std::runtime_error(e);

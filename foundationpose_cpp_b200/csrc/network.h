@@ -32,10 +32,16 @@ class WeightFile {
   const float* f32(const std::string& name, int d0, int d1 = -1) const {
     return static_cast<const float*>(get(name, 1, d0, d1).dev);
   }
+  // the same tensor in the host copy of the file (plan builders read small vectors without touching the device)
+  const float* host_f32(const std::string& name, int d0, int d1 = -1) const {
+    return reinterpret_cast<const float*>(host_.data() + (static_cast<const uint8_t*>(get(name, 1, d0, d1).dev) -
+                                                           static_cast<const uint8_t*>(blob_)));
+  }
 
  private:
   std::map<std::string, WeightTensor> tensors_;
   void* blob_ = nullptr;
+  std::vector<uint8_t> host_;
   std::string path_;
 };
 

@@ -228,6 +228,36 @@ _CONV_ORDER = (["backbone.encodeA.0.conv", "backbone.encodeA.1.conv"] +
                [f"backbone.encodeAB.{i}.conv{c}" for i in (3, 4) for c in (1, 2)])
 
 
+def canonical_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Maps the parameter names of an upstream NVlabs/FoundationPose checkpoint onto the names this module uses
+    (those of oracle/nets.py).  Upstream names, as recalled from learning/models/{refine_network,score_network,
+    network_modules}.py (no checkpoint can be fetched in this environment to confirm them):
+      * no `backbone.` prefix: `encodeA.*` / `encodeAB.*` (refiner), `encoderA.*` / `encoderAB.*` (scorer);
+      * ConvBNReLU keeps its layers in `self.net = nn.Sequential(conv, bn, relu)`: `encodeA.0.net.0.*` is the
+        convolution, `encodeA.0.net.1.*` the BatchNorm; ResnetBasicBlock uses `conv1 / bn1 / conv2 / bn2`;
+      * the positional table is the buffer `pos_embed.pe` of shape [1, 400, 512];
+      * a `module.` prefix (DataParallel) may precede everything.
+    Names that already are canonical pass through, so the function is idempotent."""
+    import re
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if k.startswith("module."):
+            k = k[7:]
+        if k.endswith("num_batches_tracked"):
+            continue
+        k = re.sub(r"^(backbone\.)?encoder(AB?)\.", r"\1encode\2.", k)  # scorer spelling
+        if re.match(r"^encode(AB?)\.", k):
+            k = "backbone." + k
+        k = re.sub(r"^(backbone\.encodeAB?\.\d+)\.net\.0\.", r"\1.conv.", k)
+        k = re.sub(r"^(backbone\.encodeAB?\.\d+)\.net\.1\.", r"\1.bn.", k)
+        if k in ("pos_embed.pe", "backbone.pos_embed.pe"):
+            k = "backbone.pe"
+        if k == "backbone.pe":
+            v = v.reshape(-1, v.shape[-1])  # [1, 400, 512] -> [400, 512]
+        out[k] = v
+    return out
+
+
 def load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
     """PyTorch checkpoint (.pth / .pt) -> flat state_dict with the upstream parameter names.
     Accepts a bare state_dict or the usual wrappers ({'model': ...}, {'state_dict': ...}) and strips a
@@ -238,21 +268,91 @@ def load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
             obj = obj[key]
     if not isinstance(obj, dict) or not all(isinstance(v, torch.Tensor) for v in obj.values()):
         raise ValueError(f"{path}: not a state_dict")
-    return {(k[7:] if k.startswith("module.") else k): v for k, v in obj.items()}
+    return canonical_state_dict(obj)
 
 
-def onnx_state_dict(path: str) -> Dict[str, torch.Tensor]:
+# dense layers in forward order with their torch shapes [out, in]: ONNX exporters turn nn.Linear / the packed MHA
+# in-projection applied to 3-D activations into MatMul(x, W^T) + Add(bias) with anonymous, transposed constants
+_DENSE_ORDER = {
+    KIND_REFINER: [(f"{h}_head.0.{n}", o, i) for h in ("trans", "rot") for n, o, i in
+                   (("self_attn.in_proj", 1536, 512), ("self_attn.out_proj", 512, 512), ("linear1", 512, 512),
+                    ("linear2", 512, 512))] ,
+    KIND_SCORER: [("att.in_proj", 1536, 512), ("att.out_proj", 512, 512), ("att_cross.in_proj", 1536, 512),
+                  ("att_cross.out_proj", 512, 512), ("linear", 1, 512)],
+}
+_DENSE_ORDER[KIND_REFINER] = (_DENSE_ORDER[KIND_REFINER][:4] + [("trans_head.1", 3, 512)] +
+                              _DENSE_ORDER[KIND_REFINER][4:] + [("rot_head.1", 3, 512)])
+
+
+def _dense_key(name: str, what: str) -> str:
+    return name + ("_weight" if what == "weight" else "_bias") if name.endswith("in_proj") else f"{name}.{what}"
+
+
+def _recover_dense(sd, inits, nodes, kind, path):
+    """Fills the dense-layer weights (and biases) of `sd` that the ONNX file holds only as anonymous MatMul / Gemm
+    constants, matched by position in graph order against _DENSE_ORDER; MatMul constants are transposed back to
+    torch's [out, in]; an in-projection exported as three 512-wide products (q, k, v slices) is concatenated back."""
+    want = _DENSE_ORDER[kind]
+    if all(_dense_key(n, "weight") in sd for n, _, _ in want):
+        return
+    consumers = {}
+    for idx, (op, ins, outs) in enumerate(nodes):
+        for i in ins:
+            consumers.setdefault(i, []).append(idx)
+    found = []  # (weight [out, in], bias or None)
+    for op, ins, outs in nodes:
+        if op not in ("MatMul", "Gemm"):
+            continue
+        const = [i for i in ins if i in inits and inits[i].ndim == 2]
+        if len(const) != 1:
+            continue  # activation x activation products of the attention itself
+        w = torch.from_numpy(np.asarray(inits[const[0]])).float()
+        w = w.t() if op == "MatMul" else w  # Gemm as exported from nn.Linear carries transB = 1
+        bias = None
+        if op == "Gemm":
+            b = [i for i in ins if i in inits and inits[i].ndim == 1]
+            bias = torch.from_numpy(np.asarray(inits[b[0]])).float() if b else None
+        else:
+            for c in consumers.get(outs[0], []):
+                cop, cins, _ = nodes[c]
+                b = [i for i in cins if i in inits and inits[i].ndim == 1]
+                if cop == "Add" and b:
+                    bias = torch.from_numpy(np.asarray(inits[b[0]])).float()
+                    break
+        found.append((w.contiguous(), bias))
+    k = 0
+    for name, o, i in want:
+        if k < len(found) and tuple(found[k][0].shape) == (o, i):
+            w, b = found[k]
+            k += 1
+        elif o == 1536 and k + 2 < len(found) and all(tuple(found[k + j][0].shape) == (512, i) for j in range(3)):
+            w = torch.cat([found[k + j][0] for j in range(3)], 0)
+            bs = [found[k + j][1] for j in range(3)]
+            b = torch.cat(bs, 0) if all(x is not None for x in bs) else None
+            k += 3
+        else:
+            got = tuple(found[k][0].shape) if k < len(found) else None
+            raise ValueError(f"{path}: dense layer '{name}' expects a [{o},{i}] weight at MatMul / Gemm #{k}, found {got}")
+        sd.setdefault(_dense_key(name, "weight"), w)
+        if b is not None:
+            sd.setdefault(_dense_key(name, "bias"), b)
+    if k != len(found):
+        raise ValueError(f"{path}: {len(found) - k} dense layers with constant weights are left over after matching")
+
+
+def onnx_state_dict(path: str, kind: int = -1) -> Dict[str, torch.Tensor]:
     """ONNX model (the refiner_hwc.onnx / scorer_hwc.onnx the reference feeds to trtexec,
     tools/cvt_onnx2trt.bash:3-15) -> state_dict with the upstream parameter names.
 
     Named initializers are taken as they are.  Convolutions whose weights lost their names because the
     exporter folded BatchNorm into them are matched BY POSITION: distinct Conv weight initializers in
     graph order = the 15 backbone convolutions in forward order (the siamese encodeA branch shares one
-    set of weights, so its second appearance is skipped).  Anything else that is missing is reported
-    by the exporter as a KeyError naming the parameter."""
+    set of weights, so its second appearance is skipped).  Dense layers whose weights became anonymous
+    transposed MatMul constants are matched by position too (_recover_dense; needs `kind`).  Anything
+    else that is missing is reported by the exporter as a KeyError naming the parameter."""
     from . import onnx_reader
     inits, nodes = onnx_reader.read_onnx(path)
-    sd = {k: torch.from_numpy(v) for k, v in inits.items() if v.dtype in (np.float32, np.float16)}
+    sd = canonical_state_dict({k: torch.from_numpy(v) for k, v in inits.items() if v.dtype in (np.float32, np.float16)})
     if _CONV_ORDER[0] + ".weight" not in sd:
         seen, convs = set(), []
         for op, ins, _ in nodes:
@@ -266,7 +366,9 @@ def onnx_state_dict(path: str) -> Dict[str, torch.Tensor]:
             sd[name + ".weight"] = w
             sd[name + ".bias"] = (torch.from_numpy(inits[ins[2]]).float() if len(ins) > 2 and ins[2] in inits
                                   else torch.zeros(w.shape[0]))
-    if "backbone.pe" not in sd:
+    if kind in _DENSE_ORDER:
+        _recover_dense(sd, inits, nodes, kind, path)
+    if "backbone.pe" not in sd or tuple(sd["backbone.pe"].shape) != (400, 512):
         sd["backbone.pe"] = positional_table()  # a pure function of the architecture, not a trained tensor
     return {k: v.float() for k, v in sd.items()}
 
@@ -274,6 +376,6 @@ def onnx_state_dict(path: str) -> Dict[str, torch.Tensor]:
 def import_weights(src: str, dst: str, kind: int) -> None:
     """src: .pth/.pt checkpoint or .onnx model of the refine (kind 0) / score (kind 1) network ->
     dst: flat FPB2W file for fpb200_create."""
-    sd = onnx_state_dict(src) if src.lower().endswith(".onnx") else load_checkpoint(src)
+    sd = onnx_state_dict(src, kind) if src.lower().endswith(".onnx") else load_checkpoint(src)
     tensors = refiner_tensors(sd) if kind == KIND_REFINER else scorer_tensors(sd)
     write_weight_file(dst, kind, tensors)

@@ -193,6 +193,14 @@ int fpb200_infer_refiner(fpb200_infer_core* core, const float* render_input, con
 int fpb200_infer_scorer(fpb200_infer_core* core, const float* render_input, const float* transf_input, int n,
                         float* scores);
 
+/* Device buffers and copies for a caller that holds the blobs but is compiled without the CUDA runtime (the
+ * `B200InferCore : inference_core::BaseInferCore` plugin in foundationpose_cpp_b200/cpp/b200_infer_core.hpp; the
+ * reference's TrtTensor does the same with cudaMalloc / cudaMemcpy, edt/inference_core/trt_core/src/trt_blob_buffer.hpp:50-191). */
+enum { FPB200_COPY_H2D = 0, FPB200_COPY_D2H = 1, FPB200_COPY_D2D = 2 };
+int fpb200_device_alloc(size_t bytes, int device, void** out);
+void fpb200_device_free(void* ptr);
+int fpb200_memcpy(void* dst, const void* src, size_t bytes, int kind);
+
 /* ---- kernel-level debug entry points (DEVICE pointers) ---- */
 enum {
   FPB200_TAPS_1X1 = 0,
@@ -240,6 +248,7 @@ typedef struct {
   float *partial, *mean_out;
   int n_hyp, mode;
   void *dbg_x1, *dbg_h, *dbg_y;
+  void* dbg_clocks; /* optional u64[24] (device): SM-clock sums of CTA 0's MMA-issuing thread and one epilogue thread per phase */
 } fpb200_encoder_desc;
 int fpb200_debug_encoder_block(const fpb200_encoder_desc* desc, int repeat, float* ms_out);
 

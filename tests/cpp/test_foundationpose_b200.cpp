@@ -42,10 +42,15 @@ class SphereLoader final : public BaseMeshLoader {
     for (int j = 0; j < stacks; ++j)
       for (int i = 0; i < slices; ++i) {
         const uint32_t a = j * (slices + 1) + i, b = a + 1, c = a + slices + 1, d = c + 1;
-        if (j > 0) faces_.push_back({a, c, b});
-        if (j < stacks - 1) faces_.push_back({b, c, d});
+        if (j > 0) faces_.push_back(make3u(a, c, b));
+        if (j < stacks - 1) faces_.push_back(make3u(b, c, d));
       }
     center_ = make3(0.2f, 0.f, 0.f);
+    // a box frame that is NOT the identity (rotation by 90 degrees about z, origin at the centroid), as the reference's
+    // PCA box would be: ConvertPoseMesh2BBox must apply it (mesh_loader.hpp:75-81)
+    dim_ = make3(2 * kRadius, 2 * kRadius, 2 * kRadius);
+    const float ob[16] = {0, 1, 0, 0, -1, 0, 0, 0, 0, 0, 1, 0, 0.2f, 0, 0, 1};  // column-major
+    std::memcpy(bounds_.data(), ob, sizeof(ob));
     tex_pixels_.resize(64 * 64 * 3);
     for (int y = 0; y < 64; ++y)
       for (int x = 0; x < 64; ++x) {
@@ -69,8 +74,10 @@ class SphereLoader final : public BaseMeshLoader {
   const std::vector<Vec3f>& GetMeshVertices() const noexcept override { return verts_; }
   const std::vector<Vec3f>& GetMeshVertexNormals() const noexcept override { return normals_; }
   const std::vector<Vec3f>& GetMeshTextureCoords() const noexcept override { return uvs_; }
-  const std::vector<std::vector<uint32_t>>& GetMeshTriangleFaces() const noexcept override { return faces_; }
+  const std::vector<Vector3ui>& GetMeshTriangleFaces() const noexcept override { return faces_; }
   const Vec3f& GetMeshModelCenter() const noexcept override { return center_; }
+  const Mat4f& GetOrientBounds() const noexcept override { return bounds_; }
+  const Vec3f& GetObjectDimension() const noexcept override { return dim_; }
   const Image& GetTextureMap() const noexcept override { return tex_; }
 
  private:
@@ -81,10 +88,16 @@ class SphereLoader final : public BaseMeshLoader {
     return Vec3f{{x, y, z}};
 #endif
   }
+  static Vector3ui make3u(uint32_t a, uint32_t b, uint32_t c) {
+    Vector3ui f;
+    f[0] = a; f[1] = b; f[2] = c;
+    return f;
+  }
   std::string name_;
   std::vector<Vec3f> verts_, normals_, uvs_;
-  std::vector<std::vector<uint32_t>> faces_;
-  Vec3f center_;
+  std::vector<Vector3ui> faces_;
+  Vec3f center_, dim_;
+  Mat4f bounds_;
   std::vector<uint8_t> tex_pixels_;
   Image tex_;
 };
@@ -185,6 +198,16 @@ int main(int argc, char** argv) {
       for (int k = 0; k < 3; ++k) dot += p[4 * k + r] * p[4 * k + c];
       CHECK(std::fabs(dot - (r == c ? 1.f : 0.f)) < 1e-3f);
     }
+  // ---- ConvertPoseMesh2BBox (mesh_loader.hpp:75-81) = pose * T(-center) * orient_bounds: here the box frame sits at the
+  // mesh centre, rotated by 90 degrees about z, so the translation is kept and the box x axis is the pose's y axis
+  {
+    const Mat4f box = ConvertPoseMesh2BBox(pose, loader);
+    const float* b = mat_data(box);
+    for (int r = 0; r < 3; ++r) {
+      CHECK(std::fabs(b[12 + r] - p[12 + r]) < 1e-5f);
+      CHECK(std::fabs(b[r] - p[4 + r]) < 1e-6f && std::fabs(b[4 + r] + p[r]) < 1e-6f && std::fabs(b[8 + r] - p[8 + r]) < 1e-6f);
+    }
+  }
   // ---- error behaviour: bool false, no throw (foundationpose.cpp:155-179, sampling.cpp:350-353)
   Mat4f dummy;
   CHECK(!model->Register(rgb, depth, mask, "no_such_target", dummy, 1));

@@ -49,3 +49,41 @@ def test_cpp_register_track_on_gpu(tmp_path):
     r = subprocess.run([exe, rp, sp, "100"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Register ok" in r.stdout
+
+
+# ---- the plugin classes against the REFERENCE's own headers (B200InferCore : inference_core::BaseInferCore, the exact
+# CreateFoundationPoseModel(refiner_core, scorer_core, loaders, K, h, w) factory).  The binary is built by
+# `make -C oracle boundary` where /root/reference exists (this container; __graft_entry__.build() does it) into
+# oracle/_ref/, which travels to the GPU box like the other checker binaries.
+REF_BOUNDARY = os.path.join(ROOT, "oracle", "_ref", "test_reference_boundary")
+
+
+def _boundary_exe():
+    if os.path.isdir("/root/reference"):
+        from foundationpose_cpp_b200 import build
+        build.build()
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "boundary"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    if not os.path.exists(REF_BOUNDARY):
+        pytest.skip("oracle/_ref/test_reference_boundary not built (needs the reference tree at build time)")
+    return REF_BOUNDARY
+
+
+def test_reference_boundary_compiles_against_reference_headers(tmp_path):
+    import torch
+    exe = _boundary_exe()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    rp, sp = _weights(tmp_path)
+    r = subprocess.run([exe, rp, sp], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 2, (r.returncode, r.stderr)
+    assert "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_boundary_register_track_syncinfer_on_gpu(tmp_path):
+    exe = _boundary_exe()
+    rp, sp = _weights(tmp_path)
+    r = subprocess.run([exe, rp, sp], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SyncInfer ok" in r.stdout and "Register ok" in r.stdout

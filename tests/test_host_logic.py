@@ -171,6 +171,37 @@ def test_obj_mesh_loader_roundtrip(tmp_path):
         mesh_loader.load_obj(q)
 
 
+def test_orient_bounds_and_bbox_pose_known_answer():
+    """GetOrientBounds / GetObjectDimension (ComputeOBB, assimp_mesh_loader.cpp:62-113) and ConvertPoseMesh2BBox
+    (mesh_loader.hpp:75-81: pose * T(-center) * orient_bounds) on a point cloud whose answer is known: a 0.1 x 0.2 x 0.4
+    box grid, rotated and shifted.  PCA axes come in ascending-variance order; signs are the solver's."""
+    from foundationpose_cpp_b200 import api
+    g = np.stack(np.meshgrid(np.linspace(-0.05, 0.05, 5), np.linspace(-0.1, 0.1, 7), np.linspace(-0.2, 0.2, 9),
+                             indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    c, s_ = np.cos(0.3), np.sin(0.3)
+    R = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]], np.float32) @ np.array([[1, 0, 0], [0, c, -s_], [0, s_, c]], np.float32)
+    shift = np.array([0.3, -0.1, 0.05], np.float32)
+    v = g @ R.T + shift
+    faces = np.array([[0, 1, 2]], np.int32)
+    ld = api.ArrayMeshLoader("box", v, np.tile([0, 0, 1.0], (len(v), 1)), np.zeros((len(v), 2)), faces,
+                             np.zeros((2, 2, 3), np.uint8))
+    ob, dim = ld.GetOrientBounds(), ld.GetObjectDimension()
+    np.testing.assert_allclose(dim, [0.1, 0.2, 0.4], atol=1e-5)
+    np.testing.assert_allclose(ob[:3, 3], shift, atol=1e-6)  # vertex mean
+    np.testing.assert_allclose(np.abs(ob[:3, :3].T @ R), np.eye(3), atol=1e-4)  # the box axes, up to sign
+    np.testing.assert_allclose(ob[3], [0, 0, 0, 1])
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, :3] = R.T
+    pose[:3, 3] = [0.0, 0.1, 0.7]
+    box = api.ConvertPoseMesh2BBox(pose, ld)
+    tf = np.eye(4, dtype=np.float32)
+    tf[:3, 3] = -ld.GetMeshModelCenter()
+    np.testing.assert_allclose(box, pose @ tf @ ob, atol=1e-6)
+    # the centre is the AABB midpoint (assimp_mesh_loader.cpp:179-180), the box origin the vertex mean: for this
+    # symmetric cloud both are `shift`, so the box pose keeps the translation of the centred-mesh pose
+    np.testing.assert_allclose(box[:3, 3], pose[:3, 3], atol=1e-5)
+
+
 def test_weight_importers_pth_and_onnx(tmp_path):
     """a .pth checkpoint and an ONNX model (named initializers, and the BN-folded form
     with anonymous Conv weights matched by position) produce the same FPB2W file as the exporter."""
@@ -216,6 +247,91 @@ def test_weight_importers_pth_and_onnx(tmp_path):
         out = tmp_path / f"folded{kind}.fpb2w"
         weights.import_weights(str(onx2), str(out), kind)
         got = weights.read_weight_file(str(out))
+        for k in want:
+            np.testing.assert_allclose(got[k].astype(np.float32), want[k].astype(np.float32), rtol=2e-3, atol=1e-6)
+
+
+def _upstream_names(sd, kind):
+    """Canonical (oracle/nets.py) names -> the names of an upstream NVlabs/FoundationPose checkpoint as recalled
+    (weights.canonical_state_dict documents them): no backbone prefix, ConvBNReLU layers under `.net.0 / .net.1`,
+    `pos_embed.pe` [1,400,512], `encoderA / encoderAB` in the score network, DataParallel prefix."""
+    import re
+    import torch
+    out = {}
+    for k, v in sd.items():
+        k = k.replace("backbone.pe", "pos_embed.pe")
+        k = re.sub(r"^backbone\.", "", k)
+        k = re.sub(r"^(encodeAB?\.\d+)\.conv\.", r"\1.net.0.", k)
+        k = re.sub(r"^(encodeAB?\.\d+)\.bn\.", r"\1.net.1.", k)
+        if kind == 1:
+            k = re.sub(r"^encode(AB?)\.", r"encoder\1.", k)
+        out["module." + k] = v[None] if k == "pos_embed.pe" else v
+        if k.endswith("running_var"):
+            out["module." + k.replace("running_var", "num_batches_tracked")] = torch.tensor(7)
+    return out
+
+
+def test_weight_importer_upstream_names_and_exported_onnx(tmp_path):
+    """(1) a checkpoint carrying the UPSTREAM parameter names imports to the same FPB2W file as the
+    exporter; (2) an ONNX file shaped like a real torch.onnx export - BatchNorm folded into anonymous Conv constants,
+    nn.Linear / packed MHA in-projection on 3-D activations turned into MatMul(x, W^T) + Add(bias) with anonymous
+    transposed constants, one in-projection split into q / k / v products, no positional table - imports to it too.
+    (`onnx` / `onnxscript` are absent from this image, so torch.onnx.export itself cannot run here: the graph is
+    built with onnx_reader.write_onnx.)"""
+    import numpy as np
+    import torch
+    from foundationpose_cpp_b200 import onnx_reader, weights
+    for kind in (weights.KIND_REFINER, weights.KIND_SCORER):
+        sd = weights.seeded_state_dict(kind, 21 + kind)
+        ref = tmp_path / f"ref{kind}.fpb2w"
+        (weights.export_refiner if kind == weights.KIND_REFINER else weights.export_scorer)(str(ref), sd)
+        want = weights.read_weight_file(str(ref))
+        # (1) upstream names
+        up = _upstream_names(sd, kind)
+        assert not any(k.startswith("module.backbone") for k in up) and "module.pos_embed.pe" in up
+        assert any(".net.0.weight" in k for k in up)
+        pth = tmp_path / f"up{kind}.pth"
+        torch.save({"model": up}, pth)
+        out = tmp_path / f"up{kind}.fpb2w"
+        weights.import_weights(str(pth), str(out), kind)
+        got = weights.read_weight_file(str(out))
+        assert got.keys() == want.keys() and all(np.array_equal(got[k], want[k]) for k in want)
+        # (2) export-shaped ONNX
+        inits, nodes, n = {}, [], 0
+        for name in weights._CONV_ORDER:
+            bn = name.replace(".conv", ".bn") if name.endswith(".conv") else name.replace("conv", "bn")
+            w, b = weights._fold(sd, name, bn)
+            inits[f"onnx::Conv_{n}"], inits[f"onnx::Conv_{n + 1}"] = w.numpy(), b.numpy()
+            nodes.append(("Conv", [f"x{n}", f"onnx::Conv_{n}", f"onnx::Conv_{n + 1}"], [f"y{n}"]))
+            if "encodeA." in name:
+                nodes.append(("Conv", [f"xb{n}", f"onnx::Conv_{n}", f"onnx::Conv_{n + 1}"], [f"yb{n}"]))
+            n += 2
+        for li, (name, o, i) in enumerate(weights._DENSE_ORDER[kind]):
+            wk, bk = weights._dense_key(name, "weight"), weights._dense_key(name, "bias")
+            w, b = sd[wk].numpy(), sd[bk].numpy()
+            if o == 1536 and li == 0:  # one in-projection exported as three sliced products
+                for j, part in enumerate("qkv"):
+                    inits[f"onnx::MatMul_{n}"] = np.ascontiguousarray(w[512 * j:512 * (j + 1)].T)
+                    inits[f"{name}.{part}_bias"] = b[512 * j:512 * (j + 1)].copy()
+                    nodes.append(("MatMul", [f"t{n}", f"onnx::MatMul_{n}"], [f"m{n}"]))
+                    nodes.append(("Add", [f"{name}.{part}_bias", f"m{n}"], [f"a{n}"]))
+                    n += 1
+            else:
+                inits[f"onnx::MatMul_{n}"] = np.ascontiguousarray(w.T)
+                inits[bk] = b
+                nodes.append(("MatMul", [f"t{n}", f"onnx::MatMul_{n}"], [f"m{n}"]))
+                nodes.append(("Add", [bk, f"m{n}"], [f"a{n}"]))
+                n += 1
+            nodes.append(("MatMul", [f"q{n}", f"k{n}"], [f"s{n}"]))  # activation x activation: must be ignored
+        for k, v in sd.items():  # LayerNorm parameters keep their names in an export
+            if ".norm" in k:
+                inits[k] = v.numpy()
+        onx = tmp_path / f"exp{kind}.onnx"
+        onnx_reader.write_onnx(str(onx), inits, nodes)
+        out = tmp_path / f"exp{kind}.fpb2w"
+        weights.import_weights(str(onx), str(out), kind)
+        got = weights.read_weight_file(str(out))
+        assert got.keys() == want.keys()
         for k in want:
             np.testing.assert_allclose(got[k].astype(np.float32), want[k].astype(np.float32), rtol=2e-3, atol=1e-6)
 

@@ -29,7 +29,19 @@ def main():
         d.partial, d.mean_out, d.n_hyp, d.mode = p(partial), p(mean), n, mode
         ms = capi.debug_encoder_block(d, repeat)
         fl = 3 * 2.0 * rows * 512 * 512
-        out["cta" if mode == 1 else "pair"] = {"ms": ms, "tflops": fl / (ms * 1e-3) / 1e12}
+        clk = torch.zeros(24, dtype=torch.int64, device="cuda")
+        d.dbg_clocks = p(clk)
+        capi.debug_encoder_block(d, 0)
+        torch.cuda.synchronize()
+        c = clk.cpu().tolist()
+        nb = max(c[6], 1)
+        names_m = ["wait accempty", "wait att k-block", "wait x1 k-block", "wait h k-block", "wait weights", "issue"]
+        names_e = ["wait slab", "wait acc G1", "wait acc G2", "wait acc G3", "passA G1", "passA G2", "passA G3",
+                   "stats exchange", "LN1 pass", "LN2 pass"]
+        out["cta" if mode == 1 else "pair"] = {
+            "ms": ms, "tflops": fl / (ms * 1e-3) / 1e12, "blocks_cta0": c[6],
+            "mma_clocks_per_block": {n: round(v / nb) for n, v in zip(names_m, c[:6])},
+            "epilogue_clocks_per_block": {n: round(v / max(c[20], 1)) for n, v in zip(names_e, c[8:18])}}
     print(json.dumps({"n_hyp": n, **out}))
 
 
