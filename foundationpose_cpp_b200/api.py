@@ -99,6 +99,14 @@ def ConvertPoseMesh2BBox(pose_in_mesh: np.ndarray, loader: BaseMeshLoader) -> np
     return np.asarray(pose_in_mesh, np.float32) @ tf @ np.asarray(loader.GetOrientBounds(), np.float32)
 
 
+def mesh_diameter_gpu(vertices, device: int = 0) -> float:
+    """CalcMeshDiameter (assimp_mesh_loader.cpp:47-60) on the device: maximum distance over all vertex pairs."""
+    v = np.ascontiguousarray(vertices, np.float32)
+    out = C.c_float(0)
+    capi.check(capi.lib().fpb200_mesh_diameter(v.ctypes.data_as(C.c_void_p), int(v.shape[0]), int(device), C.byref(out)))
+    return float(out.value)
+
+
 def _fptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost a pointer check unless a profiler injects itself
 #include <stdexcept>
 #include <string>
 
@@ -47,6 +48,17 @@ struct CudaError : std::runtime_error {
       throw std::invalid_argument(std::string(_b));                                         \
     }                                                                                       \
   } while (0)
+
+// NVTX range around a host-side stage (Nsight Systems / ncu --nvtx): the reference has no tracing at all.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define FPB_NVTX_CAT2(a, b) a##b
+#define FPB_NVTX_CAT(a, b) FPB_NVTX_CAT2(a, b)
+#define FPB_NVTX(name) ::fpb::NvtxRange FPB_NVTX_CAT(_fpb_nvtx_, __LINE__)(name)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }

@@ -792,6 +792,45 @@ void launch_repack_f32(const float* blob, int n, __half* packed, int img0, cudaS
   repack_f32_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(blob, npix, packed, img0);
 }
 
+// ---- mesh diameter --------------------------------------------------------------------------------------
+// Tiles of 256 x 256 vertex pairs (upper triangle only): the j tile is staged in shared memory, each thread keeps one
+// i vertex in registers.  dx*dx + dy*dy + dz*dz in aiVector3D::Length's order (no contraction in this file).
+namespace {
+constexpr int kDiamTile = 256;
+__global__ void __launch_bounds__(kDiamTile) mesh_diameter_kernel(const float* __restrict__ v, int n, unsigned* out_sq) {
+  // linear block index -> (ti, tj) with tj >= ti
+  const int nt = (n + kDiamTile - 1) / kDiamTile;
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+  const int tj = ti + rem;
+  __shared__ float sx[kDiamTile], sy[kDiamTile], sz[kDiamTile];
+  const int j0 = tj * kDiamTile, jn = min(kDiamTile, n - j0);
+  if ((int)threadIdx.x < jn) {
+    sx[threadIdx.x] = v[3 * (j0 + threadIdx.x)];
+    sy[threadIdx.x] = v[3 * (j0 + threadIdx.x) + 1];
+    sz[threadIdx.x] = v[3 * (j0 + threadIdx.x) + 2];
+  }
+  __syncthreads();
+  const int i = ti * kDiamTile + threadIdx.x;
+  float best = 0.f;
+  if (i < n) {
+    const float x = v[3 * i], y = v[3 * i + 1], z = v[3 * i + 2];
+    for (int j = 0; j < jn; ++j) {
+      const float dx = x - sx[j], dy = y - sy[j], dz = z - sz[j];
+      best = fmaxf(best, dx * dx + dy * dy + dz * dz);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best > 0.f) atomicMax(out_sq, __float_as_uint(best));
+}
+}  // namespace
+
+void launch_mesh_diameter(const float* vertices, int n, unsigned* out_sq, cudaStream_t s) {
+  const long long nt = (n + kDiamTile - 1) / kDiamTile;
+  const long long blocks = nt * (nt + 1) / 2;
+  mesh_diameter_kernel<<<(unsigned)blocks, kDiamTile, 0, s>>>(vertices, n, out_sq);
+}
+
 const char* preprocess_init() {
   cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kCrop * kTileRows * 8);

@@ -79,6 +79,10 @@ void launch_warp(const uint8_t* rgb, const float* xyz, int h, int w, const PoseA
 // The reference's engine blobs (f32 NHWC [n,160,160,6], foundationpose.cpp:349-354) -> packed fp16
 // network input images img0 .. img0+n-1.
 void launch_repack_f32(const float* blob, int n, __half* packed, int img0, cudaStream_t s);
+// CalcMeshDiameter (mesh_loader/assimp_mesh_loader.cpp:47-60): max pairwise vertex distance, all V^2 / 2 pairs, on the
+// device.  out_sq receives the maximum SQUARED distance as float bits (an unsigned max is exact for non-negative floats);
+// it must be zeroed by the caller; diameter = sqrtf(out_sq) (sqrt is monotone, so this equals the max of the lengths).
+void launch_mesh_diameter(const float* vertices, int n, unsigned* out_sq, cudaStream_t s);
 const char* preprocess_init();  // kernel attributes; nullptr on success
 
 }  // namespace fpb

@@ -352,6 +352,7 @@ int guard(const std::function<int()>& f) {
 }
 
 void do_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w) {
+  FPB_NVTX("fpb200/upload");
   FPB_REQUIRE(rgb && depth, "rgb/depth must not be null");
   FPB_REQUIRE(h > 0 && w > 0 && h <= s->max_h && w <= s->max_w, "image %dx%d exceeds the session maximum %dx%d", h,
               w, s->max_h, s->max_w);
@@ -369,6 +370,7 @@ void do_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h,
 }
 
 void do_xyz(fpb200_session* s) {
+  FPB_NVTX("fpb200/depth_to_xyz");
   launch_depth_to_xyz(s->depth.p, s->xyz.p, s->img_h, s->img_w, s->intr, s->stream);
   s->count_launches(1);
   s->mark(1);
@@ -383,6 +385,7 @@ void do_mask_copy(fpb200_session* s, const uint8_t* mask) {
 }
 
 void do_sample(fpb200_session* s, MeshEntry* mesh) {
+  FPB_NVTX("fpb200/sample_hypotheses");
   const int h = s->img_h, w = s->img_w;
   launch_depth_filters(s->depth.p, s->eroded.p, s->filtered.p, h, w, s->stream);
   launch_guess_translation(s->filtered.p, s->mask.p, h, w, s->intr, s->center.p, s->status.p, s->sampler_scratch.p,
@@ -396,6 +399,7 @@ void do_sample(fpb200_session* s, MeshEntry* mesh) {
 }
 
 void do_render_and_transform(fpb200_session* s, float crop_ratio) {
+  FPB_NVTX("fpb200/render_and_transform");
   FPB_REQUIRE(s->uploaded && s->cur_mesh && s->n_hyp > 0, "upload an image and set hypotheses first");
   const int nl = s->hi - s->lo;
   const MeshEntry& m = *s->cur_mesh;
@@ -409,6 +413,7 @@ void do_render_and_transform(fpb200_session* s, float crop_ratio) {
 }
 
 void do_refine_step(fpb200_session* s) {
+  FPB_NVTX("fpb200/refine_step");
   do_render_and_transform(s, kRefineCropRatio);
   const int nl = s->hi - s->lo;
   s->refiner->forward(nl, s->stream);
@@ -448,6 +453,7 @@ __global__ void unpack_exchange_kernel(const float* __restrict__ exch, float* __
 }
 
 void do_score_features(fpb200_session* s) {
+  FPB_NVTX("fpb200/score_features");
   do_render_and_transform(s, kScoreCropRatio);
   const int nl = s->hi - s->lo;
   s->scorer->forward(nl, s->stream);
@@ -475,6 +481,7 @@ void do_score_features(fpb200_session* s) {
 }
 
 void do_score_finish(fpb200_session* s) {
+  FPB_NVTX("fpb200/score_finish");
   FPB_REQUIRE(s->features_ready, "score_features must run before score_finish");
   const int n = s->n_hyp;
   const WeightFile& W = s->scorer->weights();
@@ -507,6 +514,7 @@ void enqueue_result_read(fpb200_session* s) {
 }
 
 int wait_result(fpb200_session* s, float out_pose[16], int* best_index) {
+  FPB_NVTX("fpb200/wait_result");
   FPB_CUDA(cudaStreamSynchronize(s->stream));
   s->pending_async = false;
   const int st = s->host_result->status;
@@ -634,8 +642,7 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
     for (int i = 0; i < num_meshes; ++i) {
       const fpb200_mesh& m = meshes[i];
       FPB_REQUIRE(m.name && m.vertices && m.normals && m.texcoords && m.faces && m.texture, "mesh %d: null field", i);
-      FPB_REQUIRE(m.num_vertices > 0 && m.num_faces > 0 && m.tex_h > 0 && m.tex_w > 0 && m.diameter > 0,
-                  "mesh %d: empty geometry / texture", i);
+      FPB_REQUIRE(m.num_vertices > 0 && m.num_faces > 0 && m.tex_h > 0 && m.tex_w > 0, "mesh %d: empty geometry / texture", i);
       FPB_REQUIRE(!s->find_mesh(m.name), "duplicate mesh name '%s'", m.name);
       std::unique_ptr<MeshEntry> e(new MeshEntry);
       e->name = m.name;
@@ -655,8 +662,22 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
       e->texcoords.upload(tc.data(), tc.size());
       e->texture.upload(tex.data(), tex.size());
       e->faces.upload(m.faces, (size_t)m.num_faces * 3);
+      float diameter = m.diameter;
+      if (!(diameter > 0)) {  // not supplied by the loader: all-pairs maximum on the device (translation-invariant)
+        DevBuf<unsigned> sq;
+        sq.alloc(1);
+        FPB_CUDA(cudaMemsetAsync(sq.p, 0, sizeof(unsigned), s->stream));
+        launch_mesh_diameter(e->vertices.p, m.num_vertices, sq.p, s->stream);
+        unsigned bits = 0;
+        FPB_CUDA(cudaMemcpyAsync(&bits, sq.p, sizeof(bits), cudaMemcpyDeviceToHost, s->stream));
+        FPB_CUDA(cudaStreamSynchronize(s->stream));
+        float d2;
+        memcpy(&d2, &bits, sizeof(d2));
+        diameter = sqrtf(d2);
+        FPB_REQUIRE(diameter > 0, "mesh %d: all vertices coincide", i);
+      }
       e->dm = DeviceMesh{e->vertices.p, e->normals.p, e->texcoords.p, e->faces.p, e->texture.p,
-                         m.num_vertices, m.num_faces, m.tex_h, m.tex_w, m.diameter};
+                         m.num_vertices, m.num_faces, m.tex_h, m.tex_w, diameter};
       s->meshes.push_back(std::move(e));
     }
 
@@ -702,6 +723,29 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
   });
 }
 
+int fpb200_mesh_diameter(const float* vertices, int num_vertices, int device, float* diameter) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(vertices && diameter && num_vertices > 0, "null / empty argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      throw CudaError("no CUDA device available: this library has no CPU fallback");
+    FPB_CUDA(cudaSetDevice(device));
+    DevBuf<float> v;
+    DevBuf<unsigned> sq;
+    v.upload(vertices, (size_t)num_vertices * 3);
+    sq.alloc(1);
+    FPB_CUDA(cudaMemset(sq.p, 0, sizeof(unsigned)));
+    launch_mesh_diameter(v.p, num_vertices, sq.p, nullptr);
+    FPB_CUDA(cudaGetLastError());
+    unsigned bits = 0;
+    FPB_CUDA(cudaMemcpy(&bits, sq.p, sizeof(bits), cudaMemcpyDeviceToHost));
+    float d2;
+    memcpy(&d2, &bits, sizeof(d2));
+    *diameter = sqrtf(d2);
+    return FPB200_OK;
+  });
+}
+
 void fpb200_destroy(fpb200_session* s) {
   if (!s) return;
   cudaStreamSynchronize(s->stream);
@@ -710,6 +754,7 @@ void fpb200_destroy(fpb200_session* s) {
 
 int fpb200_register(fpb200_session* s, const uint8_t* rgb, const float* depth, const uint8_t* mask, int h, int w,
                     const char* target_name, int refine_itr, float out_pose[16]) {
+  FPB_NVTX("fpb200_register");
   return guard([&]() -> int {
     FPB_REQUIRE(s && out_pose, "null session / output");
     FPB_REQUIRE(s->opt.shard_world == 1 || s->exchange_ready,
@@ -743,6 +788,7 @@ int fpb200_register(fpb200_session* s, const uint8_t* rgb, const float* depth, c
 }
 
 int fpb200_register_async(fpb200_session* s, const char* target_name, int refine_itr) {
+  FPB_NVTX("fpb200_register_async");
   return guard([&]() -> int {
     FPB_REQUIRE(s, "null session");
     FPB_REQUIRE(s->opt.shard_world == 1 || s->exchange_ready,
@@ -771,6 +817,7 @@ int fpb200_register_async(fpb200_session* s, const char* target_name, int refine
 
 int fpb200_track_async(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w,
                        const float hyp_pose[16], const char* target_name, int refine_itr) {
+  FPB_NVTX("fpb200_track_async");
   return guard([&]() -> int {
     FPB_REQUIRE(s && hyp_pose, "null session / pose");
     MeshEntry* mesh = s->find_mesh(target_name);

@@ -61,6 +61,11 @@ typedef struct {
 
 void fpb200_default_options(fpb200_options* o);
 
+/* CalcMeshDiameter of the reference's loader (fp/src/mesh_loader/assimp_mesh_loader.cpp:47-60: the maximum distance
+ * over ALL vertex pairs, O(V^2) on one CPU core there) evaluated on the device.  vertices: HOST [n,3] f32.
+ * fpb200_create calls it for every mesh whose `diameter` field is <= 0. */
+int fpb200_mesh_diameter(const float* vertices, int num_vertices, int device, float* diameter);
+
 /* Replaces CreateFoundationPoseModel (fp/include/.../foundationpose.hpp:99-105) together with the
  * two CreateTrtInferCore calls that feed it (edt/inference_core/trt_core/include/trt_core/trt_core.h:26-30):
  * the weight files take the place of the serialized TensorRT engines. */

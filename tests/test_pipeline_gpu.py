@@ -298,3 +298,38 @@ def test_infer_core_boundary(tmp_path):
     lib.fpb200_infer_destroy(core)
     bad = C.c_void_p()
     assert lib.fpb200_infer_create(rp.encode(), 1, 8, 0, C.byref(bad)) != 0  # refiner file given as scorer
+
+
+def test_mesh_diameter_on_device_matches_all_pairs_maximum(tmp_path):
+    """CalcMeshDiameter (assimp_mesh_loader.cpp:47-60, maximum over ALL vertex pairs) on the device.
+    Float32 all-pairs maximum in numpy (the reference's arithmetic: differences, squares, sum, sqrt) on 2 210 and on
+    5 252 vertices (ragged last tile); a session created with diameter <= 0 computes the same value itself."""
+    from foundationpose_cpp_b200 import mesh_loader
+    for mesh in (synth.uv_ellipsoid("a", slices=64, stacks=33, tex_size=32, seed=1),
+                 synth.uv_ellipsoid("b", slices=100, stacks=51, axes=(0.08, 0.08, 0.1), tex_size=32, seed=2)):
+        v = np.ascontiguousarray(mesh.vertices, F)
+        best = F(0)
+        for i in range(0, len(v), 1024):
+            d = v[i:i + 1024, None, :] - v[None, :, :]
+            best = max(best, (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]).max())
+        want = float(np.sqrt(F(best)))
+        got = api.mesh_diameter_gpu(v)
+        assert got == want, (got, want)  # bit-exact: same fp32 operations, max is order-independent
+        assert abs(got - mesh_loader.max_pairwise_distance(v)) < 1e-6
+    rp, sp = helpers.write_seeded_weights(str(tmp_path))
+    ld = api.ArrayMeshLoader.from_mesh_data(mesh)
+    ld._d = 0.0  # "not supplied": fpb200_create computes it
+    m0 = api.CreateFoundationPoseModel(rp, sp, [ld], synth.DEFAULT_K, max_h=480, max_w=640, max_hyps=4)
+    ld._d = got
+    m1 = api.CreateFoundationPoseModel(rp, sp, [ld], synth.DEFAULT_K, max_h=480, max_w=640, max_hyps=4)
+    rgb, depth, mask, gt = synth.make_scene(mesh)
+    try:
+        outs = []
+        for m in (m0, m1):
+            ok, pose = m.Track(rgb, depth, gt, mesh.name, refine_itr=1)
+            assert ok, m.last_error
+            outs.append(pose)
+        assert np.array_equal(outs[0], outs[1])
+    finally:
+        m0.close()
+        m1.close()
