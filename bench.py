@@ -71,11 +71,37 @@ def scene(kind: str = "mustard", seed: int = 0):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock / power / throttle reasons of one GPU, sampled DURING the timed region: NVML in-process (a thread polling
+    every 5 ms: works for timed regions of a few tens of ms and with 8 ranks starting at once), `nvidia-smi -lms 20`
+    as a fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.rows, self.proc = [], None
+    def __init__(self, index: int, uuid: str = None):
+        self.rows, self.proc, self.nvml, self.stop_flag, self.mx = [], None, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand if isinstance(cand, bytes) else cand.encode())
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.handle = pynvml, h
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
@@ -84,35 +110,49 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = [(n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else n.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)), "hw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)), "sw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)), "sw_power_cap")]
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append((time.time(), sm, pw, [nm for b, nm in bits if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0: float, t1: float):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons, pw = [], None, set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [(ts, line) for ts, line in self.rows if t0 - 0.05 <= ts <= t1 + 0.05]
-        if not inside:  # timed region shorter than the sampling period: take the samples closest to it
-            inside = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
-        for ts, line in inside:
-            f = [x.strip() for x in line.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-                pw.append(float(f[2]))
+                self.mx = float(f[1])
+                self.rows.append((time.time(), float(f[0]), float(f[2]),
+                                  [nm for nm, v in zip(self.NAMES, f[3:7]) if v.lower().startswith("active")]))
             except Exception:
                 continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        pw.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None}
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc and not self.nvml:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
+        time.sleep(0.05)
+        self.stop_flag = True
+        if self.proc:
+            time.sleep(0.1)
+            self.proc.terminate()
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not inside:  # timed region shorter than the sampling period: take the samples closest to it
+            inside = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
+        sm = sorted(r[1] for r in inside)
+        pw = sorted(r[2] for r in inside)
+        reasons = sorted({nm for r in inside for nm in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None,
+                "source": "NVML in-process, 5 ms period" if self.nvml else "nvidia-smi -lms 20"}
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
@@ -507,7 +547,11 @@ def main():
 
     # ---- warm-up (also makes rgb/depth/mask resident); the clock sampler starts now so that it is already
     # streaming when the (possibly very short) timed region begins
-    clocks = ClockSampler(local_rank)
+    try:
+        _uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        _uuid = None
+    clocks = ClockSampler(local_rank, _uuid)
     model.set_async(sw > 1 and not p2p)
     warm = max(args.warmup, 3)
     for _ in range(warm):

@@ -599,6 +599,36 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   const long long m_tiles_all = (long long)((d.out_w + d.bw - 1) / d.bw) * ((d.out_h + d.bh - 1) / d.bh) *
                                 ((d.n_img + d.bn - 1) / d.bn);
   int mode = d.cluster > 0 ? (d.cluster == 1 ? 0 : 2) : (m_tiles_all >= 2 * g_num_sms ? 2 : 0);
+  // Multi-tap (deep-K) layers between one and a few waves of tiles - a rank's share of a sharded Register, 31..126
+  // hypotheses - are dominated by wave quantisation: e.g. the 512-channel layers at 32 hypotheses have 100 row tiles,
+  // i.e. 200 tiles of width 256 on 148 SMs = 2 waves for 1.35 waves of work.  Every (width, pairing) candidate is
+  // costed as waves x tile width x a measured per-column penalty (B200, tools/scratch sweep of every layer shape at
+  // 31 / 32 / 63 / 126 hypotheses: narrow tiles on single CTAs pay 1.5-1.6x per column for the repeated activation
+  // traffic, CTA pairs do not) and the rule above is overridden when a candidate is predicted > 5 % faster.
+  // Measured: 512 -> 512 at 32 hypotheses 55 -> 43 us (128 wide, paired), 256 -> 512 / s2 at 63: 52 -> 44 us.
+  if (d.num_taps > 1 && !d.block_n && d.cluster == 0 && !getenv("FPB_GEMM_BN") && !getenv("FPB_GEMM_MODE") &&
+      m_tiles_all * (d.cout / 64) >= 2LL * g_num_sms) {
+    auto cost = [&](int bn, int md) -> double {
+      const long long items = (md ? (m_tiles_all + 1) / 2 : m_tiles_all) * (d.cout / bn);
+      const long long slots = md ? g_num_sms / 2 : g_num_sms;
+      const long long waves = (items + slots - 1) / slots;
+      double pen = bn == 256 ? (md ? 0.94 : 1.0) : bn == 128 ? (md ? 1.0 : 1.5) : (md ? 1.4 : 1.6);
+      if (d.planes > 1 && bn < 256) pen *= 1.3;  // phase-split (stride-2) inputs: more, smaller activation boxes
+      return (double)waves * bn * pen;
+    };
+    double best = cost(bn_tile, mode ? 1 : 0);
+    const double keep = best;
+    int best_bn = bn_tile, best_mode = mode;
+    for (int bn : {256, 128, 64}) {
+      if (d.cout % bn) continue;
+      for (int md : {1, 0}) {
+        if (md && m_tiles_all < 2) continue;
+        const double c = cost(bn, md);
+        if (c < best) { best = c; best_bn = bn; best_mode = md ? 2 : 0; }
+      }
+    }
+    if (best < 0.95 * keep) { bn_tile = best_bn; mode = best_mode; }
+  }
   if (d.cluster == 0)
     if (const char* env = getenv("FPB_GEMM_MODE")) mode = atoi(env) ? 2 : 0;
   const int cluster = mode == 0 ? 1 : 2;

@@ -179,42 +179,51 @@ token_mean_kernel(const __half* __restrict__ x, float* __restrict__ out) {
 }
 
 // out[rows, outs] = in[rows, k] * w[outs, k]^T + b, fp32 (the scorer tail after the token mean: 252 rows).
-// 32 x 32 output tile per 256-thread CTA (so a 252 x 512 product spreads over 128 CTAs), K in chunks
-// of 32 through double-buffered shared memory; thread (ty, tx) owns row ty and outputs tx, tx+8, tx+16,
-// tx+24 and walks k four at a time with 16-byte shared loads (row pitch 36 floats: the eight lanes of
-// a quarter-warp hit disjoint banks, the row operand is a broadcast).  Sums run in ascending k.
-constexpr int kSGTile = 32, kSGChunk = 32, kSGPitch = kSGChunk + 4;
+// 32 x 32 output tile per 256-thread CTA (so a 252 x 512 product spreads over 128 CTAs); thread (ty, tx)
+// owns row ty and outputs tx, tx+8, tx+16, tx+24 and walks k four at a time with 16-byte shared loads
+// (row pitch 132 floats: the eight lanes of a quarter-warp hit disjoint banks, the row operand is a
+// broadcast).  Sums run in ascending k.
+// Staging: K chunks of 128 floats through a 4-stage cp.async ring (for K = 512 every load of the CTA is in flight at
+// once: the kernel costs one memory round trip plus ~3 us of FMAs instead of 16 dependent chunk round trips).
+constexpr int kSGTile = 32, kSGChunk = 128, kSGPitch = kSGChunk + 4, kSGStages = 4;
+constexpr size_t kSmallLinearSmem = sizeof(float) * kSGStages * 2 * kSGTile * kSGPitch;
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b,
                     float* __restrict__ out, int rows, int k, int outs) {
-  __shared__ __align__(16) float s_a[2][kSGTile * kSGPitch];
-  __shared__ __align__(16) float s_w[2][kSGTile * kSGPitch];
+  extern __shared__ __align__(16) float s_lin[];  // [stage][a | w][32 x pitch]
   const int r0 = blockIdx.x * kSGTile, o0 = blockIdx.y * kSGTile;
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  // loader mapping: thread -> (tile row lr, 16-byte column lc) of both tiles
-  const int lr = threadIdx.x >> 3, lc = (threadIdx.x & 7) * 4;
-  const bool a_ok = r0 + lr < rows, w_ok = o0 + lr < outs;
-  const float* a_src = in + static_cast<long long>(a_ok ? r0 + lr : 0) * k + lc;
-  const float* w_src = w + static_cast<long long>(w_ok ? o0 + lr : 0) * k + lc;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto fetch = [&](int kc, float4& av, float4& wv) {
-    const bool in_k = kc + lc < k;  // k is a multiple of 4 (checked by the launcher)
-    av = (a_ok && in_k) ? __ldg(reinterpret_cast<const float4*>(a_src + kc)) : zero4;
-    wv = (w_ok && in_k) ? __ldg(reinterpret_cast<const float4*>(w_src + kc)) : zero4;
-  };
-  float4 av, wv;
-  fetch(0, av, wv);
-  *reinterpret_cast<float4*>(&s_a[0][lr * kSGPitch + lc]) = av;
-  *reinterpret_cast<float4*>(&s_w[0][lr * kSGPitch + lc]) = wv;
-  __syncthreads();
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const int n_chunks = (k + kSGChunk - 1) / kSGChunk;
-  for (int c = 0; c < n_chunks; ++c) {
-    const int cur = c & 1;
-    if (c + 1 < n_chunks) fetch((c + 1) * kSGChunk, av, wv);
-    const float* pa = &s_a[cur][ty * kSGPitch];
-    const float* pw = &s_w[cur][tx * kSGPitch];
+  auto issue = [&](int c) {
+    if (c < n_chunks) {
+      float* sa = s_lin + (size_t)(c % kSGStages) * 2 * kSGTile * kSGPitch;
+      float* sw = sa + kSGTile * kSGPitch;
+      const int kc = c * kSGChunk;
 #pragma unroll
+      for (int i = threadIdx.x; i < kSGTile * (kSGChunk / 4); i += 256) {
+        const int lr = i >> 5, lc = (i & 31) * 4;
+        const bool in_k = kc + lc < k;  // k is a multiple of 4 (checked by the launcher)
+        const bool a_ok = r0 + lr < rows && in_k, w_ok = o0 + lr < outs && in_k;
+        cp_async16(sa + lr * kSGPitch + lc, in + static_cast<long long>(a_ok ? r0 + lr : 0) * k + (in_k ? kc + lc : 0), a_ok);
+        cp_async16(sw + lr * kSGPitch + lc, w + static_cast<long long>(w_ok ? o0 + lr : 0) * k + (in_k ? kc + lc : 0), w_ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // (possibly empty: keeps the group count uniform)
+  };
+#pragma unroll
+  for (int c = 0; c < kSGStages; ++c) issue(c);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < n_chunks; ++c) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kSGStages - 1) : "memory");
+    __syncthreads();
+    const float* pa = s_lin + (size_t)(c % kSGStages) * 2 * kSGTile * kSGPitch + ty * kSGPitch;
+    const float* pw = s_lin + (size_t)(c % kSGStages) * 2 * kSGTile * kSGPitch + kSGTile * kSGPitch + tx * kSGPitch;
+#pragma unroll 8
     for (int kk = 0; kk < kSGChunk; kk += 4) {
       const float4 a4 = *reinterpret_cast<const float4*>(pa + kk);
 #pragma unroll
@@ -226,11 +235,8 @@ small_linear_kernel(const float* __restrict__ in, const float* __restrict__ w, c
         acc[j] = fmaf(a4.w, w4.w, acc[j]);
       }
     }
-    if (c + 1 < n_chunks) {
-      *reinterpret_cast<float4*>(&s_a[cur ^ 1][lr * kSGPitch + lc]) = av;
-      *reinterpret_cast<float4*>(&s_w[cur ^ 1][lr * kSGPitch + lc]) = wv;
-    }
-    __syncthreads();
+    __syncthreads();  // the slot is refilled by chunk c + stages
+    issue(c + kSGStages);
   }
   if (r0 + ty < rows) {
 #pragma unroll
@@ -445,6 +451,9 @@ const char* net_ops_init() {
   if (cudaFuncSetAttribute(cross_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrossAttnMaxSmem) !=
       cudaSuccess)
     return "cudaFuncSetAttribute(cross_attention smem) failed (not an sm_100a device?)";
+  if (cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallLinearSmem) !=
+      cudaSuccess)
+    return "cudaFuncSetAttribute(small_linear smem) failed (not an sm_100a device?)";
   return nullptr;
 }
 
@@ -483,7 +492,7 @@ void launch_small_linear(const float* in, const float* w, const float* b, float*
     return;
   }
   dim3 grid((rows + kSGTile - 1) / kSGTile, (outs + kSGTile - 1) / kSGTile);
-  small_linear_kernel<<<grid, 256, 0, s>>>(in, w, b, out, rows, k, outs);
+  small_linear_kernel<<<grid, 256, kSmallLinearSmem, s>>>(in, w, b, out, rows, k, outs);
 }
 
 void launch_cross_attention(const float* qkv, float* out, int n, cudaStream_t s) {

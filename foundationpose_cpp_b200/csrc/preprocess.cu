@@ -672,16 +672,17 @@ __device__ __forceinline__ void shade_pixels(const DeviceMesh& mesh, const PoseA
 __global__ void __launch_bounds__(kBandThreads, 2)
 render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vclip,
               const float4* __restrict__ vattr, __half* __restrict__ packed, int img0,
-              int32_t* __restrict__ rast_id_debug, int* __restrict__ status) {
+              int32_t* __restrict__ rast_id_debug, int* __restrict__ status, int experiment) {
   extern __shared__ unsigned long long zbuf[];  // [kTileRows * 160]
   const int pose = blockIdx.y;
   const int row0 = blockIdx.x * kTileRows;  // GL rows [row0, row0 + kTileRows)
   for (int i = threadIdx.x; i < kCrop * kTileRows; i += blockDim.x) zbuf[i] = ~0ull;
   __syncthreads();
   const float4* pc = vclip + (long long)pose * mesh.num_vertices;
-  if (raster_triangles(mesh, pc, threadIdx.x, blockDim.x, row0, kTileRows, zbuf)) atomicOr(status, kStatusClipPath);
+  if (experiment != 1)
+    if (raster_triangles(mesh, pc, threadIdx.x, blockDim.x, row0, kTileRows, zbuf)) atomicOr(status, kStatusClipPath);
   __syncthreads();
-  shade_pixels(mesh, aux_all, pc, vattr, packed, img0, rast_id_debug, pose, row0, kTileRows, zbuf);
+  if (experiment != 2) shade_pixels(mesh, aux_all, pc, vattr, packed, img0, rast_id_debug, pose, row0, kTileRows, zbuf);
 }
 
 // Few hypotheses (Track: one): a (band, hypothesis) grid would leave most SMs idle while 4 CTAs walk all
@@ -889,8 +890,10 @@ int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vcl
                                                                              rast_id_debug, zbuf_scratch, kShadeRows);
     return 3;
   }
+  static const int experiment = getenv("FPB200_RENDER_EXPERIMENT") ? atoi(getenv("FPB200_RENDER_EXPERIMENT")) : 0;
+  if (experiment == 3) return 1;
   render_kernel<<<dim3(kRenderTiles, n), kBandThreads, kCrop * kTileRows * 8, s>>>(mesh, aux, vclip, vattr, packed,
-                                                                                      img0, rast_id_debug, status);
+                                                                                      img0, rast_id_debug, status, experiment);
   return 2;
 }
 

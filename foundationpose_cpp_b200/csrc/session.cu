@@ -249,6 +249,10 @@ struct fpb200_session {
   int max_h = 0, max_w = 0;
   Intrinsics intr{};
   cudaStream_t stream = nullptr;
+  // side branch: the observed-crop warp does not depend on the rasteriser, so it runs beside it (fork / join with
+  // events; inside a capture this becomes a parallel branch of the CUDA graph)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[kNumStages + 1]{};
   bool ev_valid[kNumStages + 1]{};
   std::vector<std::unique_ptr<MeshEntry>> meshes;
@@ -307,6 +311,9 @@ struct fpb200_session {
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
     if (host_result) cudaFreeHost(host_result);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side_stream) cudaStreamDestroy(side_stream);
     if (stream) cudaStreamDestroy(stream);
   }
   MeshEntry* find_mesh(const char* name) {
@@ -404,10 +411,15 @@ void do_render_and_transform(fpb200_session* s, float crop_ratio) {
   const int nl = s->hi - s->lo;
   const MeshEntry& m = *s->cur_mesh;
   launch_pose_setup(s->poses.p + 16 * s->lo, nl, s->intr, m.dm.diameter, crop_ratio, s->aux.p, s->stream);
+  // fork: warp (HBM-bound, reads the frame) beside the rasteriser (latency-bound, reads the mesh); both only need aux
+  FPB_CUDA(cudaEventRecord(s->ev_fork, s->stream));
+  FPB_CUDA(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
+  launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->side_stream);
+  FPB_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
   const int k_render = launch_render(m.dm, s->aux.p, nl, s->vclip.p, s->vattr.p, s->arena->packed, 0,
                                      s->debug_ids ? s->rast_id.p : nullptr, s->status.p, s->zbuf.p, kSplitRenderPoses,
                                      s->num_sms, s->render_split, s->stream);
-  launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->stream);
+  FPB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_join, 0));  // join before the networks read both halves of `packed`
   s->count_launches(2 + k_render);
   s->crop_ratio_last = crop_ratio;
 }
@@ -636,6 +648,9 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
       for (int i = 0; i < 9; ++i) s->intr.kinv[i] = (float)inv[i];
     }
     FPB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    FPB_CUDA(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+    FPB_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    FPB_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     for (auto& e : s->ev) FPB_CUDA(cudaEventCreate(&e));
     FPB_CUDA(cudaMallocHost(&s->host_result, sizeof(HostResult)));
 

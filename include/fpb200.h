@@ -134,7 +134,10 @@ int fpb200_score_finish(fpb200_session* s, int* best_index, float out_pose[16]);
  * shard, stores its rows straight into every peer's region and ranks all N redundantly, so every rank returns
  * the same pose.  All ranks must make the same sequence of Register calls (a missing peer is reported as
  * FPB200_ERR_STATE after ~2 s, never a hang).  fpb200_exchange_connect_local does the same for sessions that
- * live in ONE process (tests; several GPUs driven by one host thread). */
+ * live in ONE process (tests; several GPUs driven by one host thread).  Ranks that SHARE a device spin-wait for each
+ * other inside kernels, so each of their streams (2 per session) needs a hardware queue of its own: with more than 3
+ * such sessions set CUDA_DEVICE_MAX_CONNECTIONS >= 2 * world + 2 before CUDA initialises (default 8), otherwise an
+ * aliased queue parks a peer's kernels behind a spinning one and the call reports the exchange time-out. */
 #define FPB200_IPC_HANDLE_BYTES 64
 int fpb200_exchange_export(fpb200_session* s, unsigned char handle[FPB200_IPC_HANDLE_BYTES]);
 int fpb200_exchange_connect(fpb200_session* s, const unsigned char* handles /* [shard_world][64], rank order */);

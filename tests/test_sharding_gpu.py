@@ -5,9 +5,16 @@ every rank's score_finish must return the unsharded session's winner.  Per-hypot
 on which other hypotheses share a launch (fixed K-loop order per output element), so equality is exact.
 The reference has no multi-GPU path; the scorer's cross-hypothesis attention
  is why features, not scores, are exchanged."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
+
+for _p in (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__)))):
+    if _p not in sys.path:  # also runnable as a script (the world = 8 case, see below)
+        sys.path.insert(0, _p)
 
 from foundationpose_cpp_b200 import api, sharding, synth
 import fp_helpers as helpers
@@ -85,13 +92,7 @@ def test_sharded_register_equals_single_session(setup, world):
         assert np.array_equal(pose, setup["pose"])
 
 
-@pytest.mark.parametrize("world", [2, 8])
-def test_peer_memory_exchange_register_equals_single_session(setup, world):
-    """The in-library exchange (fpb200_exchange_*: rows stored straight into every rank's region, arrival flags,
-    no collective call): `world` sharded sessions of ONE process on one GPU, wired with
-    fpb200_exchange_connect_local, each run the public register_async; every rank must return the unsharded
-    session's winner, scores and pose bit for bit - eagerly, while capturing, and from the replayed CUDA graph
-    (the exchange is double-buffered by epoch parity, so back-to-back calls are covered too)."""
+def _peer_exchange_body(setup, world):
     ms = [setup["make"](r, world) for r in range(world)]
     try:
         api.connect_local(ms)
@@ -114,3 +115,51 @@ def test_peer_memory_exchange_register_equals_single_session(setup, world):
     finally:
         for m in ms:
             m.close()
+
+
+def test_peer_memory_exchange_register_equals_single_session(setup):
+    """The in-library exchange (fpb200_exchange_*: rows stored straight into every rank's region, arrival flags,
+    no collective call): 2 sharded sessions of ONE process on one GPU, wired with fpb200_exchange_connect_local,
+    each run the public register_async; every rank must return the unsharded session's winner, scores and pose bit
+    for bit - eagerly, while capturing, and from the replayed CUDA graph (the exchange is double-buffered by epoch
+    parity, so back-to-back calls are covered too)."""
+    _peer_exchange_body(setup, 2)
+
+
+def test_peer_memory_exchange_world8_in_a_subprocess():
+    """The same with 8 ranks.  Ranks that share ONE device (a test-only topology: the product runs one process per
+    GPU) spin-wait for each other inside kernels, so every session stream must own a hardware queue: 8 sessions x 2
+    streams exceed the driver's default of 8 connections, and an aliased queue would park a peer's kernels behind a
+    spinning one (reported as 'exchange timed out' after 2 s, never a hang).  CUDA_DEVICE_MAX_CONNECTIONS has to be
+    set before the CUDA context exists, hence the fresh process (fpb200.h documents the requirement)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "8"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "peer exchange world 8 ok" in r.stdout
+
+
+if __name__ == "__main__":
+    import os
+    import sys
+    import tempfile
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    _world = int(sys.argv[1])
+    _d = tempfile.mkdtemp()
+    _rp, _sp = helpers.write_seeded_weights(_d)
+    _mesh = synth.uv_ellipsoid("obj", slices=64, stacks=33, tex_size=256, seed=0)
+    _rgb, _depth, _mask, _ = synth.make_scene(_mesh)
+
+    def _make(rank, world):
+        return api.CreateFoundationPoseModel(_rp, _sp, [api.ArrayMeshLoader.from_mesh_data(_mesh)], synth.DEFAULT_K,
+                                             max_h=480, max_w=640, max_hyps=N, shard_rank=rank, shard_world=world)
+
+    _ref = _make(0, 1)
+    _ok, _pose = _ref.Register(_rgb, _depth, _mask, "obj", refine_itr=1)
+    assert _ok, _ref.last_error
+    _scores = _ref.read_buffer("scores", np.float32, N).copy()
+    _ref.close()
+    _peer_exchange_body({"make": _make, "rgb": _rgb, "depth": _depth, "mask": _mask, "pose": _pose, "scores": _scores}, _world)
+    print(f"peer exchange world {_world} ok")
