@@ -60,6 +60,19 @@ struct NvtxRange {
 #define FPB_NVTX_CAT(a, b) FPB_NVTX_CAT2(a, b)
 #define FPB_NVTX(name) ::fpb::NvtxRange FPB_NVTX_CAT(_fpb_nvtx_, __LINE__)(name)
 
+// The CUDA runtime loads a kernel lazily at its first launch; that load is a device-wide operation which waits for
+// running kernels (seen as a 2 s stall of every stream when the first Register of one session met the spinning exchange
+// wait of another).  Querying the attributes at create time loads the function then.
+template <typename... K>
+inline cudaError_t preload_kernels(K... kernels) {
+  cudaError_t err = cudaSuccess;
+  cudaFuncAttributes a;
+  const cudaError_t rs[] = {cudaFuncGetAttributes(&a, kernels)...};
+  for (cudaError_t r : rs)
+    if (r != cudaSuccess) err = r;
+  return err;
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -37,6 +37,8 @@
 // of how many hypotheses share a launch and of where a hypothesis starts (sharded runs stay bit-identical).
 #include "encoder_block.h"
 
+#include "common.h"
+
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -647,6 +649,7 @@ const char* encoder_block_init() {
   set_attr(encoder_block_kernel<true, false>, Cfg<true>::kSmem);
   set_attr(encoder_block_kernel<false, true>, Cfg<false>::kSmem);
   set_attr(encoder_block_kernel<true, true>, Cfg<true>::kSmem);
+  if (e == cudaSuccess) e = preload_kernels(encoder_mean_kernel);
   if (e != cudaSuccess)
     return "cudaFuncSetAttribute(encoder_block smem) failed (not an sm_100a device?)";
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);

@@ -1,6 +1,8 @@
 // Non-GEMM network operators (see net_ops.h).  All HBM-bound or tiny; fp32 math, fp16 storage.
 #include "net_ops.h"
 
+#include "common.h"
+
 #include <cfloat>
 #include <stdexcept>
 
@@ -454,6 +456,9 @@ const char* net_ops_init() {
   if (cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallLinearSmem) !=
       cudaSuccess)
     return "cudaFuncSetAttribute(small_linear smem) failed (not an sm_100a device?)";
+  if (preload_kernels(layernorm_kernel, layernorm_mean_kernel, layernorm_mean_combine_kernel, token_mean_kernel,
+                      row_dot_kernel, argmax_pose_kernel, refine_update_kernel) != cudaSuccess)
+    return "loading the network helper kernels failed (not an sm_100a device?)";
   return nullptr;
 }
 

@@ -121,6 +121,7 @@ Network::Network(NetKind kind, const std::string& weight_path, Arena* arena)
   if (const char* e = attention_init()) throw std::runtime_error(e);
   if (const char* e = net_ops_init()) throw std::runtime_error(e);
   if (const char* e = encoder_block_init()) throw std::runtime_error(e);
+  if (const char* e = encoder_block_init()) throw std::runtime_error(e);
   flops_per_hyp_ = plan(1).flops;
 }
 

@@ -3,6 +3,8 @@
 // This translation unit is compiled with -fmad=false: expressions round exactly as written.
 #include "preprocess.h"
 
+#include "common.h"
+
 #include <cfloat>
 #include <cstdlib>
 
@@ -314,10 +316,8 @@ __global__ void pose_setup_kernel(const float* __restrict__ poses, int n, Intrin
 
 // ------------------------------------------------------------------ render
 constexpr int kRenderThreads = 256;                  // split-path kernels
-constexpr int kBandThreads = 512;                    // band kernel
-constexpr int kRenderTiles = 2;                      // horizontal bands per hypothesis: every band CTA walks all
-                                                     // triangles, so fewer, larger bands repeat less set-up work
-constexpr int kTileRows = kCrop / kRenderTiles;      // 80 rows -> 102 KB z-buffer, 2 CTAs (32 warps) per SM
+// band kernel: 2 bands of 80 rows per hypothesis (512 threads, 102 KB z-buffer, 2 CTAs = 32 warps per SM) or one band
+// of 160 rows (1024 threads, 205 KB); every band CTA walks all triangles
 constexpr unsigned kDepthMin = 2200u << 3;
 constexpr unsigned kDepthMax = 0xFFFFFFFFu - (2200u << 3);
 
@@ -325,8 +325,9 @@ constexpr unsigned kDepthMax = 0xFFFFFFFFu - (2200u << 3);
 // (generate_pose_clip_kernel, foundationpose_render.cu:363-398), camera-space position
 // (transform_points_kernel, :321-341) and headlight diffuse term (transform_normals_kernel, :418-443).
 // The reference keeps these as three [N,V,*] fp32 tensors too (pose_clip, pts_cam, diffuse).
-__global__ void vertex_stage_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all,
-                                    float4* __restrict__ vclip, float4* __restrict__ vattr) {
+// Output: one 32-byte record per (hypothesis, vertex): {clip position, (camera-space position, diffuse)} - the
+// rasteriser reads the first half, a shaded pixel both halves of its three vertices as three 32-byte sectors.
+__global__ void vertex_stage_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, float4* __restrict__ vrec) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   const int pose = blockIdx.y;
   if (v >= mesh.num_vertices) return;
@@ -352,9 +353,9 @@ __global__ void vertex_stage_kernel(DeviceMesh mesh, const PoseAux* __restrict__
   const float l2 = sqrtf((nx * nx + ny * ny) + nz * nz);
   const float val = l2 == 0.f ? 0.f : -nz / l2;
   q.w = fminf(fmaxf(val, 0.f), 1.f);
-  const long long o = (long long)pose * mesh.num_vertices + v;
-  vclip[o] = c;
-  vattr[o] = q;
+  const long long o = 2 * ((long long)pose * mesh.num_vertices + v);
+  vrec[o] = c;
+  vrec[o + 1] = q;
 }
 
 __device__ __forceinline__ int snap(float v) {
@@ -389,12 +390,32 @@ __device__ __forceinline__ void setup_pleq(float z0, float z1, float z2, int v0x
   pl[2] = z;
 }
 
+// z-buffer update "nearest wins, later triangle wins ties" (FineRaster.inl:152-172,338-351) on the key
+// (u32 depth << 32) | ~triangle.  Shared memory has no native 64-bit minimum (atomicMin compiles to a compare-and-swap
+// loop that always swaps), so the slot is read first and the swap only attempted while the key still wins: occluded
+// samples cost one load.  Global memory: one fire-and-forget REDG.MIN.64.
+template <bool kSharedZ>
+__device__ __forceinline__ void zbuf_min(unsigned long long* slot, unsigned long long key) {
+  if (kSharedZ) {
+    unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(slot);
+    while (key < old) {
+      const unsigned long long assumed = old;
+      old = atomicCAS(slot, assumed, key);
+      if (old == assumed) break;
+    }
+  } else {
+    atomicMin(slot, key);
+  }
+}
+
 // One snapped (sub)triangle of triangle t inside GL rows [row0, row0 + nrows): cudaraster's depth plane
-// (setupTriangle, TriangleSetup.inl:120-177), exact coverage with its fill rule (Util.inl:304-309) and a
-// 64-bit atomicMin per covered sample on a z-buffer (shared or global memory, row pitch 160) whose key is
-// (u32 depth << 32) | ~triangle: nearest wins and on equal depth the later triangle wins
-// (FineRaster.inl:152-172,338-351), whatever the order in which triangles arrive.  `live` = false makes
-// the call a no-op (callers keep their warps converged instead of branching around it).
+// (setupTriangle, TriangleSetup.inl:120-177), exact coverage with its fill rule (Util.inl:304-309) and one z-buffer
+// update per covered sample (shared or global memory, row pitch 160), whatever the order in which triangles arrive.
+// The samples of the bounding box are walked as ONE flat loop (a warp runs max-over-lanes of the box areas instead
+// of the sum of its distinct rows) with the three edge functions and the depth stepped by additions: the same 64-bit
+// integers as evaluating them per sample.  `live` = false makes the call a no-op (callers keep their warps converged
+// instead of branching around it).
+template <bool kSharedZ>
 __device__ __forceinline__ void raster_piece(bool live, int p0x, int p0y, int p1x, int p1y, int p2x, int p2y, float z0,
                                              float z1, float z2, float rw0, float rw1, float rw2, int t, int row0,
                                              int nrows, unsigned long long* zbuf) {
@@ -432,19 +453,32 @@ __device__ __forceinline__ void raster_piece(bool live, int p0x, int p0y, int p1
     const long long adj1 = (e1y > 0 || (e1y == 0 && e1x <= 0)) ? 1 : 0;
     const long long adj2 = (e2y > 0 || (e2y == 0 && e2x <= 0)) ? 1 : 0;
     const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - (unsigned)t);
-    for (int py = py0; py <= py1; ++py) {
-      const int sy = py * 16 - bias;
-      for (int px = px0; px <= px1; ++px) {
-        const int sx = px * 16 - bias;
-        const long long v0 = (long long)(p0x - sx) * e0y - (long long)(p0y - sy) * e0x - adj0;
-        const long long v1 = (long long)(p1x - sx) * e1y - (long long)(p1y - sy) * e1x - adj1;
-        const long long v2 = (long long)(p0x - sx) * e2y - (long long)(p0y - sy) * e2x - adj2;
-        if ((v0 | v1 | v2) >= 0) {
-          const unsigned depth = pl[0] * (unsigned)px + pl[1] * (unsigned)py + pl[2];
-          // depth > kDepthMax would lie behind the cleared depth (FineRaster.inl:338)
-          if (depth <= kDepthMax) atomicMin(&zbuf[(py - row0) * W + px], ((unsigned long long)depth << 32) | low);
-        }
-      }
+    // edge functions at the first sample of the box; one pixel to the right: sx += 16, one row down: sy += 16
+    const int sx0 = px0 * 16 - bias, sy0 = py0 * 16 - bias;
+    long long v0 = (long long)(p0x - sx0) * e0y - (long long)(p0y - sy0) * e0x - adj0;
+    long long v1 = (long long)(p1x - sx0) * e1y - (long long)(p1y - sy0) * e1x - adj1;
+    long long v2 = (long long)(p0x - sx0) * e2y - (long long)(p0y - sy0) * e2x - adj2;
+    const int bw = px1 - px0 + 1;
+    const long long s0x = -16LL * e0y, s1x = -16LL * e1y, s2x = -16LL * e2y;
+    // step at the end of a row: back to the first column and one row down (selected, not branched to: the loop then
+    // has one data-dependent branch per sample - the z-buffer update - instead of three)
+    const long long s0w = 16LL * e0x - (long long)(bw - 1) * s0x, s1w = 16LL * e1x - (long long)(bw - 1) * s1x,
+                    s2w = 16LL * e2x - (long long)(bw - 1) * s2x;
+    unsigned depth = pl[0] * (unsigned)px0 + pl[1] * (unsigned)py0 + pl[2];
+    const unsigned dstep_w = pl[1] - pl[0] * (unsigned)(bw - 1);
+    unsigned long long* slot = zbuf + (py0 - row0) * W + px0;
+    const int n_samples = bw * (py1 - py0 + 1);
+    int x = 0;
+    for (int k = 0; k < n_samples; ++k) {
+      // depth > kDepthMax would lie behind the cleared depth (FineRaster.inl:338)
+      if ((v0 | v1 | v2) >= 0 && depth <= kDepthMax) zbuf_min<kSharedZ>(slot, ((unsigned long long)depth << 32) | low);
+      const bool wrap = ++x == bw;
+      v0 += wrap ? s0w : s0x;
+      v1 += wrap ? s1w : s1x;
+      v2 += wrap ? s2w : s2x;
+      depth += wrap ? dstep_w : pl[0];
+      slot += wrap ? W - bw + 1 : 1;
+      x = wrap ? 0 : x;
     }
   }
 }
@@ -480,6 +514,7 @@ __device__ __forceinline__ int clip_poly_plane(float* out, const float* in, int 
   }
   return num_out >> 1;
 }
+template <bool kSharedZ>
 __device__ __noinline__ void raster_clipped(float4 A, float4 B, float4 C, int t, int row0, int nrows,
                                             unsigned long long* zbuf) {
   const float a[4] = {A.x, A.y, A.z, A.w};
@@ -507,9 +542,9 @@ __device__ __noinline__ void raster_clipped(float4 A, float4 B, float4 C, int t,
   for (int i = 2; i < num; ++i) {
     for (int k = 0; k < 4; ++k) v2[k] = fmaf(d2[k], bary[i * 2 + 1], fmaf(d1[k], bary[i * 2 + 0], a[k]));
     const float rw0 = 1.0f / v0[3], rw1 = 1.0f / v1[3], rw2 = 1.0f / v2[3];
-    raster_piece(true, snap(v0[0] * rw0 * vs), snap(v0[1] * rw0 * vs), snap(v1[0] * rw1 * vs), snap(v1[1] * rw1 * vs),
-                 snap(v2[0] * rw2 * vs), snap(v2[1] * rw2 * vs), v0[2], v1[2], v2[2], rw0, rw1, rw2, t, row0, nrows,
-                 zbuf);
+    raster_piece<kSharedZ>(true, snap(v0[0] * rw0 * vs), snap(v0[1] * rw0 * vs), snap(v1[0] * rw1 * vs),
+                           snap(v1[1] * rw1 * vs), snap(v2[0] * rw2 * vs), snap(v2[1] * rw2 * vs), v0[2], v1[2], v2[2], rw0,
+                           rw1, rw2, t, row0, nrows, zbuf);
     for (int k = 0; k < 4; ++k) v1[k] = v2[k];
   }
 }
@@ -517,6 +552,7 @@ __device__ __noinline__ void raster_clipped(float4 A, float4 B, float4 C, int t,
 // Visibility of the triangles t = t_first + i * t_stride (i = 0, 1, ...) inside GL rows [row0, row0 + nrows)
 // of one hypothesis: cudaraster's triangle setup (TriangleSetup.inl:181-391; fast path inline, clip path in
 // raster_clipped) and raster_piece per snapped triangle.  Returns whether some triangle took the clip path.
+template <bool kSharedZ>
 __device__ __forceinline__ bool raster_triangles(const DeviceMesh& mesh, const float4* __restrict__ pc, int t_first,
                                                  int t_stride, int row0, int nrows, unsigned long long* zbuf) {
   constexpr int W = kCrop;
@@ -531,17 +567,18 @@ __device__ __forceinline__ bool raster_triangles(const DeviceMesh& mesh, const f
     bool live = t < mesh.num_faces;
     int i0 = 0, i1 = 0, i2 = 0;
     if (live) {
-      i0 = mesh.faces[3 * t];
-      i1 = mesh.faces[3 * t + 1];
-      i2 = mesh.faces[3 * t + 2];
+      const int4 f = mesh.faces[t];
+      i0 = f.x;
+      i1 = f.y;
+      i2 = f.z;
       live = (unsigned)i0 < (unsigned)mesh.num_vertices && (unsigned)i1 < (unsigned)mesh.num_vertices &&
              (unsigned)i2 < (unsigned)mesh.num_vertices;
     }
     float4 A = make_float4(0.f, 0.f, 0.f, 1.f), B = A, C = A;
     if (live) {
-      A = pc[i0];
-      B = pc[i1];
-      C = pc[i2];
+      A = pc[2 * i0];
+      B = pc[2 * i1];
+      C = pc[2 * i2];
     }
     if (live && ((A.w < fabsf(A.x)) | (A.w < fabsf(A.y)) | (A.w < fabsf(A.z)))) {
       if (((A.w < +A.x) & (B.w < +B.x) & (C.w < +C.x)) | ((A.w < -A.x) & (B.w < -B.x) & (C.w < -C.x)) |
@@ -564,33 +601,127 @@ __device__ __forceinline__ bool raster_triangles(const DeviceMesh& mesh, const f
       clipped = true;  // outside the S16 snap range / too large for the guard band
       live = false;
     }
-    raster_piece(live, p0x, p0y, p1x, p1y, p2x, p2y, A.z, B.z, C.z, rw0, rw1, rw2, t, row0, nrows, zbuf);
+    raster_piece<kSharedZ>(live, p0x, p0y, p1x, p1y, p2x, p2y, A.z, B.z, C.z, rw0, rw1, rw2, t, row0, nrows, zbuf);
     if (clipped) {
       // rare: the vertices are fetched again here (through a different load path, so that the compiler cannot
       // keep the 12 floats above alive across the pixel loop of the fast path)
       clip_path = true;
-      const int j0 = __ldcg(mesh.faces + 3 * t), j1 = __ldcg(mesh.faces + 3 * t + 1), j2 = __ldcg(mesh.faces + 3 * t + 2);
-      raster_clipped(__ldcg(pc + j0), __ldcg(pc + j1), __ldcg(pc + j2), t, row0, nrows, zbuf);
+      const int4 f = __ldcg(mesh.faces + t);
+      raster_clipped<kSharedZ>(__ldcg(pc + 2 * f.x), __ldcg(pc + 2 * f.y), __ldcg(pc + 2 * f.z), t, row0, nrows, zbuf);
     }
     __syncwarp();
   }
   return clip_path;
 }
 
-// Per pixel of GL rows [row0, row0 + nrows) (z-buffer row pitch 160, first row = row0): nvdiffrast's
-// barycentrics / interpolation / texture (rasterize.cu:55-89, interpolate.cu:46-76, texture.cu:19-96), the
-// reference's shading (foundationpose_render.cu:459-501), vertical flip (foundationpose_render.cpp:676-680),
-// normalisation and packing (foundationpose_render.cu:61-140).
-__device__ __forceinline__ void shade_pixels(const DeviceMesh& mesh, const PoseAux* __restrict__ aux_all,
-                                             const float4* __restrict__ pc, const float4* __restrict__ vattr,
-                                             __half* __restrict__ packed, int img0, int32_t* __restrict__ rast_id_debug,
-                                             int pose, int row0, int nrows, const unsigned long long* zbuf) {
+// One covered pixel (px, GL row py) of triangle `tri`: nvdiffrast's barycentrics / interpolation / texture
+// (rasterize.cu:55-89, interpolate.cu:46-76, texture.cu:19-96), the reference's shading
+// (foundationpose_render.cu:459-501), normalisation and packing (foundationpose_render.cu:61-140).  Returns the packed
+// 8-channel fp16 pixel.
+struct ShadeCtx {
+  const float4* rec;  // vertex records of this hypothesis: [v][0] clip position, [v][1] camera-space position + diffuse
+  float t_x, t_y, t_z, half_d;
+};
+__device__ __forceinline__ uint4 pack_pixel(const float* o) {
+  uint4 pk;
+  __half2* hp = reinterpret_cast<__half2*>(&pk);
+  hp[0] = __floats2half2_rn(o[0], o[1]);
+  hp[1] = __floats2half2_rn(o[2], o[3]);
+  hp[2] = __floats2half2_rn(o[4], o[5]);
+  hp[3] = __floats2half2_rn(0.f, 0.f);
+  return pk;
+}
+__device__ __forceinline__ uint4 shade_one(const DeviceMesh& mesh, const ShadeCtx& c, int tri, int px, int py) {
   constexpr int W = kCrop, H = kCrop;
   const float xs = 2.0f / (float)W, xo = 1.0f / (float)W - 1.0f;
   const float ys = 2.0f / (float)H, yo = 1.0f / (float)H - 1.0f;
-  const float half_d = mesh.diameter / 2.f;
-  const float4* pa = vattr + (long long)pose * mesh.num_vertices;
-  const float t_x = aux_all[pose].t[0], t_y = aux_all[pose].t[1], t_z = aux_all[pose].t[2];
+  const int4 f = mesh.faces[tri];
+  const int i0 = f.x, i1 = f.y, i2 = f.z;
+  const float4 p0 = c.rec[2 * i0], p1 = c.rec[2 * i1], p2 = c.rec[2 * i2];
+  const float4 q0 = c.rec[2 * i0 + 1], q1 = c.rec[2 * i1 + 1], q2 = c.rec[2 * i2 + 1];
+  const float2 t0 = *reinterpret_cast<const float2*>(mesh.texcoords + 2 * i0);
+  const float2 t1 = *reinterpret_cast<const float2*>(mesh.texcoords + 2 * i1);
+  const float2 t2 = *reinterpret_cast<const float2*>(mesh.texcoords + 2 * i2);
+  const float fx = xs * (float)px + xo;
+  const float fy = ys * (float)py + yo;
+  const float p0x = p0.x - fx * p0.w, p0y = p0.y - fy * p0.w;
+  const float p1x = p1.x - fx * p1.w, p1y = p1.y - fy * p1.w;
+  const float p2x = p2.x - fx * p2.w, p2y = p2.y - fy * p2.w;
+  const float a0 = p1x * p2y - p1y * p2x;
+  const float a1 = p2x * p0y - p2y * p0x;
+  const float a2 = p0x * p1y - p0y * p1x;
+  const float iw = 1.f / ((a0 + a1) + a2);
+  const float b0 = __saturatef(a0 * iw);
+  const float b1 = __saturatef(a1 * iw);
+  const float b2 = (1.f - b0) - b1;
+  const float xyz0 = (b0 * q0.x + b1 * q1.x) + b2 * q2.x;
+  const float xyz1 = (b0 * q0.y + b1 * q1.y) + b2 * q2.y;
+  const float xyz2 = (b0 * q0.z + b1 * q1.z) + b2 * q2.z;
+  const float dif = (b0 * q0.w + b1 * q1.w) + b2 * q2.w;
+  float u = (b0 * t0.x + b1 * t1.x) + b2 * t2.x;
+  float v = (b0 * t0.y + b1 * t1.y) + b2 * t2.y;
+  // bilinear texture fetch, wrap
+  const int tw = mesh.tex_w, th = mesh.tex_h;
+  u = u - floorf(u);
+  v = v - floorf(v);
+  u = u * (float)tw - 0.5f;
+  v = v * (float)th - 0.5f;
+  int iu0 = (int)floorf(u), iv0 = (int)floorf(v);
+  int iu1 = iu0 + 1, iv1 = iv0 + 1;
+  const float fu = u - (float)iu0, fv = v - (float)iv0;
+  if (iu0 < 0) iu0 += tw;
+  if (iv0 < 0) iv0 += th;
+  if (iu1 >= tw) iu1 -= tw;
+  if (iv1 >= th) iv1 -= th;
+  const float4 c00 = mesh.texture[(long long)iv0 * tw + iu0];
+  const float4 c10 = mesh.texture[(long long)iv0 * tw + iu1];
+  const float4 c01 = mesh.texture[(long long)iv1 * tw + iu0];
+  const float4 c11 = mesh.texture[(long long)iv1 * tw + iu1];
+  const float light = 0.8f + dif * 0.5f;
+  float o[6];
+  {
+    const float k00[3] = {c00.x, c00.y, c00.z}, k10[3] = {c10.x, c10.y, c10.z};
+    const float k01[3] = {c01.x, c01.y, c01.z}, k11[3] = {c11.x, c11.y, c11.z};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float top = k00[ch] + fu * (k10[ch] - k00[ch]);
+      const float bot = k01[ch] + fu * (k11[ch] - k01[ch]);
+      const float col = top + fv * (bot - top);
+      o[ch] = fminf(fmaxf(col * light, 0.f), 1.f);
+    }
+  }
+  // normalise (threshold_and_downscale_pointcloud_kernel)
+  const bool invalid = xyz2 < kMinDepth;
+  const float qx = (xyz0 - c.t_x) / c.half_d, qy = (xyz1 - c.t_y) / c.half_d, qz = (xyz2 - c.t_z) / c.half_d;
+  o[3] = (invalid || fabsf(qx) > kMaxDepth) ? 0.f : qx;
+  o[4] = (invalid || fabsf(qy) > kMaxDepth) ? 0.f : qy;
+  o[5] = (invalid || fabsf(qz) > kMaxDepth) ? 0.f : qz;
+  return pack_pixel(o);
+}
+__device__ __forceinline__ ShadeCtx make_shade_ctx(const DeviceMesh& mesh, const PoseAux* __restrict__ aux_all,
+                                                   const float4* pc, int pose) {
+  ShadeCtx c;
+  c.rec = pc;
+  c.t_x = aux_all[pose].t[0];
+  c.t_y = aux_all[pose].t[1];
+  c.t_z = aux_all[pose].t[2];
+  c.half_d = mesh.diameter / 2.f;
+  return c;
+}
+
+// Pixel i = (GL row row0 + i / 160, column i % 160) of the packed image of `pose`, vertically flipped
+// (foundationpose_render.cpp:676-680).
+__device__ __forceinline__ uint4* packed_pixel(__half* img, int py, int px) {
+  return reinterpret_cast<uint4*>(img + ((long long)(kCrop - 1 - py) * kStemPitch + kStemPad + px) * kPackC);
+}
+
+// Split path: every thread shades its pixels of GL rows [row0, row0 + nrows) straight from the global z-buffer.
+__device__ __forceinline__ void shade_pixels(const DeviceMesh& mesh, const PoseAux* __restrict__ aux_all,
+                                             const float4* __restrict__ pc, __half* __restrict__ packed, int img0,
+                                             int32_t* __restrict__ rast_id_debug, int pose, int row0, int nrows,
+                                             const unsigned long long* zbuf) {
+  constexpr int W = kCrop, H = kCrop;
+  const ShadeCtx c = make_shade_ctx(mesh, aux_all, pc, pose);
   __half* img = packed + (long long)(img0 + pose) * kPackImageElems;
   for (int i = threadIdx.x; i < W * nrows; i += blockDim.x) {
     const int ly = i / W, px = i - ly * W;
@@ -598,113 +729,108 @@ __device__ __forceinline__ void shade_pixels(const DeviceMesh& mesh, const PoseA
     const unsigned long long key = zbuf[i];
     const int tri = key == ~0ull ? -1 : (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
     if (rast_id_debug) rast_id_debug[(long long)pose * W * H + py * W + px] = tri + 1;
-    float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (tri >= 0) {
-      const int i0 = mesh.faces[3 * tri], i1 = mesh.faces[3 * tri + 1], i2 = mesh.faces[3 * tri + 2];
-      const float4 p0 = pc[i0], p1 = pc[i1], p2 = pc[i2];
-      const float4 q0 = pa[i0], q1 = pa[i1], q2 = pa[i2];
-      const float fx = xs * (float)px + xo;
-      const float fy = ys * (float)py + yo;
-      const float p0x = p0.x - fx * p0.w, p0y = p0.y - fy * p0.w;
-      const float p1x = p1.x - fx * p1.w, p1y = p1.y - fy * p1.w;
-      const float p2x = p2.x - fx * p2.w, p2y = p2.y - fy * p2.w;
-      const float a0 = p1x * p2y - p1y * p2x;
-      const float a1 = p2x * p0y - p2y * p0x;
-      const float a2 = p0x * p1y - p0y * p1x;
-      const float iw = 1.f / ((a0 + a1) + a2);
-      const float b0 = __saturatef(a0 * iw);
-      const float b1 = __saturatef(a1 * iw);
-      const float b2 = (1.f - b0) - b1;
-      const float xyz0 = (b0 * q0.x + b1 * q1.x) + b2 * q2.x;
-      const float xyz1 = (b0 * q0.y + b1 * q1.y) + b2 * q2.y;
-      const float xyz2 = (b0 * q0.z + b1 * q1.z) + b2 * q2.z;
-      const float dif = (b0 * q0.w + b1 * q1.w) + b2 * q2.w;
-      const float2 t0 = *reinterpret_cast<const float2*>(mesh.texcoords + 2 * i0);
-      const float2 t1 = *reinterpret_cast<const float2*>(mesh.texcoords + 2 * i1);
-      const float2 t2 = *reinterpret_cast<const float2*>(mesh.texcoords + 2 * i2);
-      float u = (b0 * t0.x + b1 * t1.x) + b2 * t2.x;
-      float v = (b0 * t0.y + b1 * t1.y) + b2 * t2.y;
-      // bilinear texture fetch, wrap
-      const int tw = mesh.tex_w, th = mesh.tex_h;
-      u = u - floorf(u);
-      v = v - floorf(v);
-      u = u * (float)tw - 0.5f;
-      v = v * (float)th - 0.5f;
-      int iu0 = (int)floorf(u), iv0 = (int)floorf(v);
-      int iu1 = iu0 + 1, iv1 = iv0 + 1;
-      const float fu = u - (float)iu0, fv = v - (float)iv0;
-      if (iu0 < 0) iu0 += tw;
-      if (iv0 < 0) iv0 += th;
-      if (iu1 >= tw) iu1 -= tw;
-      if (iv1 >= th) iv1 -= th;
-      const float* c00 = mesh.texture + 3 * ((long long)iv0 * tw + iu0);
-      const float* c10 = mesh.texture + 3 * ((long long)iv0 * tw + iu1);
-      const float* c01 = mesh.texture + 3 * ((long long)iv1 * tw + iu0);
-      const float* c11 = mesh.texture + 3 * ((long long)iv1 * tw + iu1);
-      const float light = 0.8f + dif * 0.5f;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const float top = c00[ch] + fu * (c10[ch] - c00[ch]);
-        const float bot = c01[ch] + fu * (c11[ch] - c01[ch]);
-        const float col = top + fv * (bot - top);
-        o[ch] = fminf(fmaxf(col * light, 0.f), 1.f);
-      }
-      // normalise (threshold_and_downscale_pointcloud_kernel)
-      const bool invalid = xyz2 < kMinDepth;
-      const float qx = (xyz0 - t_x) / half_d, qy = (xyz1 - t_y) / half_d, qz = (xyz2 - t_z) / half_d;
-      o[3] = (invalid || fabsf(qx) > kMaxDepth) ? 0.f : qx;
-      o[4] = (invalid || fabsf(qy) > kMaxDepth) ? 0.f : qy;
-      o[5] = (invalid || fabsf(qz) > kMaxDepth) ? 0.f : qz;
-    }
-    const int yimg = H - 1 - py;
-    uint4 pk;
-    __half2* hp = reinterpret_cast<__half2*>(&pk);
-    hp[0] = __floats2half2_rn(o[0], o[1]);
-    hp[1] = __floats2half2_rn(o[2], o[3]);
-    hp[2] = __floats2half2_rn(o[4], o[5]);
-    hp[3] = __floats2half2_rn(0.f, 0.f);
-    *reinterpret_cast<uint4*>(img + ((long long)yimg * kStemPitch + kStemPad + px) * kPackC) = pk;
+    *packed_pixel(img, py, px) = tri >= 0 ? shade_one(mesh, c, tri, px, py) : make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
-// One CTA per (band of 40 rows, hypothesis): every thread takes triangles and resolves visibility on a
-// shared-memory z-buffer (raster_triangles), then the band is shaded (shade_pixels).
-__global__ void __launch_bounds__(kBandThreads, 2)
-render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vclip,
-              const float4* __restrict__ vattr, __half* __restrict__ packed, int img0,
+// Band path (shared-memory z-buffer): covered pixels are COMPACTED first, so that the long dependent-load chain of
+// shade_one (z-buffer -> face -> vertices -> texels) is spread evenly over all threads: with a typical 26 % of the crop
+// covered, a thread shades ~6 pixels instead of up to 25 while most warps only wrote zeros.  The list of covered pixel
+// indices is stored in the UPPER halves of the first `count` z-buffer entries (the depth words, dead after
+// rasterisation; the triangle ids in the lower halves stay in place), so it needs no memory of its own.
+template <int kThreads, int kRows>
+__device__ __forceinline__ void shade_band_compacted(const DeviceMesh& mesh, const PoseAux* __restrict__ aux_all,
+                                                     const float4* __restrict__ pc, __half* __restrict__ packed, int img0,
+                                                     int32_t* __restrict__ rast_id_debug, int pose, int row0,
+                                                     unsigned long long* zbuf, int* count) {
+  constexpr int W = kCrop, H = kCrop, kPixels = W * kRows;
+  static_assert(kPixels % kThreads == 0 && kPixels / kThreads <= 32, "one coverage bit per owned pixel");
+  constexpr int kIter = kPixels / kThreads;
+  __half* img = packed + (long long)(img0 + pose) * kPackImageElems;
+  // A: coverage bits of the pixels this thread owns; empty pixels are written (zeros) right away
+  unsigned mask = 0;
+#pragma unroll 5
+  for (int it = 0; it < kIter; ++it) {
+    const int i = it * kThreads + threadIdx.x;
+    const unsigned long long key = zbuf[i];
+    const bool covered = key != ~0ull;
+    const int ly = i / W, px = i - ly * W;
+    if (rast_id_debug)
+      rast_id_debug[(long long)pose * W * H + (row0 + ly) * W + px] = covered ? (int)(0xFFFFFFFFu - (unsigned)key) + 1 : 0;
+    if (covered) mask |= 1u << it;
+    else *packed_pixel(img, row0 + ly, px) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();  // every key has been read: the depth words may be overwritten
+  // B: append the covered pixel indices (warp-aggregated)
+  unsigned* words = reinterpret_cast<unsigned*>(zbuf);
+  const unsigned lane = threadIdx.x & 31u;
+  for (int it = 0; it < kIter; ++it) {
+    const bool covered = (mask >> it) & 1u;
+    const unsigned vote = __ballot_sync(0xffffffffu, covered);
+    if (vote == 0u) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, __popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (covered) words[2 * (base + __popc(vote & ((1u << lane) - 1u))) + 1] = (unsigned)(it * kThreads + threadIdx.x);
+  }
+  __syncthreads();
+  // C: shade the list
+  const int n_covered = *count;
+  const ShadeCtx c = make_shade_ctx(mesh, aux_all, pc, pose);
+  for (int j = threadIdx.x; j < n_covered; j += kThreads) {
+    const int i = (int)words[2 * j + 1];
+    const int tri = (int)(0xFFFFFFFFu - words[2 * i]);
+    const int ly = i / W, px = i - ly * W;
+    *packed_pixel(img, row0 + ly, px) = shade_one(mesh, c, tri, px, row0 + ly);
+  }
+}
+
+// One CTA per (band of kRows rows, hypothesis): every thread takes triangles and resolves visibility on a
+// shared-memory z-buffer (raster_triangles), then the band is shaded (shade_band_compacted).
+template <int kThreads, int kRows>
+__global__ void __launch_bounds__(kThreads, 1024 / kThreads)
+render_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vrec,
+              __half* __restrict__ packed, int img0,
               int32_t* __restrict__ rast_id_debug, int* __restrict__ status, int experiment) {
-  extern __shared__ unsigned long long zbuf[];  // [kTileRows * 160]
+  extern __shared__ unsigned long long zbuf[];  // [kRows * 160]
+  __shared__ int covered_count;
   const int pose = blockIdx.y;
-  const int row0 = blockIdx.x * kTileRows;  // GL rows [row0, row0 + kTileRows)
-  for (int i = threadIdx.x; i < kCrop * kTileRows; i += blockDim.x) zbuf[i] = ~0ull;
+  const int row0 = blockIdx.x * kRows;  // GL rows [row0, row0 + kRows)
+  for (int i = threadIdx.x; i < kCrop * kRows; i += kThreads) zbuf[i] = ~0ull;
+  if (threadIdx.x == 0) covered_count = 0;
   __syncthreads();
-  const float4* pc = vclip + (long long)pose * mesh.num_vertices;
+  const float4* pc = vrec + 2 * (long long)pose * mesh.num_vertices;
   if (experiment != 1)
-    if (raster_triangles(mesh, pc, threadIdx.x, blockDim.x, row0, kTileRows, zbuf)) atomicOr(status, kStatusClipPath);
+    if (raster_triangles<true>(mesh, pc, threadIdx.x, kThreads, row0, kRows, zbuf)) atomicOr(status, kStatusClipPath);
   __syncthreads();
-  if (experiment != 2) shade_pixels(mesh, aux_all, pc, vattr, packed, img0, rast_id_debug, pose, row0, kTileRows, zbuf);
+  if (experiment != 2)
+    shade_band_compacted<kThreads, kRows>(mesh, aux_all, pc, packed, img0, rast_id_debug, pose, row0, zbuf,
+                                          &covered_count);
 }
 
 // Few hypotheses (Track: one): a (band, hypothesis) grid would leave most SMs idle while 4 CTAs walk all
 // triangles, so the triangles are spread over blockIdx.x CTAs as well, on a global z-buffer of the whole
 // crop (pre-set to ~0), and the crop is shaded by a second kernel.  Same keys, same atomicMin: the
 // visibility result is identical to render_kernel's.
+__global__ void fill_u64_kernel(unsigned long long* p, long long n, unsigned long long v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
 __global__ void __launch_bounds__(kRenderThreads)
-raster_split_kernel(DeviceMesh mesh, const float4* __restrict__ vclip, unsigned long long* __restrict__ zbuf_all,
+raster_split_kernel(DeviceMesh mesh, const float4* __restrict__ vrec, unsigned long long* __restrict__ zbuf_all,
                     int* __restrict__ status) {
   const int pose = blockIdx.y;
-  const float4* pc = vclip + (long long)pose * mesh.num_vertices;
-  if (raster_triangles(mesh, pc, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, 0, kCrop,
-                       zbuf_all + (long long)pose * kCrop * kCrop))
+  const float4* pc = vrec + 2 * (long long)pose * mesh.num_vertices;
+  if (raster_triangles<false>(mesh, pc, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, 0, kCrop,
+                              zbuf_all + (long long)pose * kCrop * kCrop))
     atomicOr(status, kStatusClipPath);
 }
 __global__ void __launch_bounds__(kRenderThreads)
-shade_split_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vclip,
-                   const float4* __restrict__ vattr, __half* __restrict__ packed, int img0,
+shade_split_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, const float4* __restrict__ vrec,
+                   __half* __restrict__ packed, int img0,
                    int32_t* __restrict__ rast_id_debug, const unsigned long long* __restrict__ zbuf_all, int rows) {
   const int pose = blockIdx.y;
   const int row0 = blockIdx.x * rows;
-  shade_pixels(mesh, aux_all, vclip + (long long)pose * mesh.num_vertices, vattr, packed, img0, rast_id_debug, pose,
+  shade_pixels(mesh, aux_all, vrec + 2 * (long long)pose * mesh.num_vertices, packed, img0, rast_id_debug, pose,
                row0, rows, zbuf_all + (long long)pose * kCrop * kCrop + (long long)row0 * kCrop);
 }
 
@@ -833,9 +959,15 @@ void launch_mesh_diameter(const float* vertices, int n, unsigned* out_sq, cudaSt
 }
 
 const char* preprocess_init() {
-  cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kCrop * kTileRows * 8);
-  return e == cudaSuccess ? nullptr : "cudaFuncSetAttribute(render_kernel smem) failed";
+  cudaError_t e = cudaFuncSetAttribute(render_kernel<512, kCrop / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kCrop * (kCrop / 2) * 8);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(render_kernel<1024, kCrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrop * kCrop * 8);
+  if (e != cudaSuccess) return "cudaFuncSetAttribute(render_kernel smem) failed";
+  e = preload_kernels(depth_to_xyz_kernel, erode_depth_kernel, bilateral_depth_kernel, sampler_init_kernel, mask_scan_kernel,
+                      median_select_kernel, fill_hypotheses_kernel, pose_setup_kernel, vertex_stage_kernel, fill_u64_kernel,
+                      raster_split_kernel, shade_split_kernel, warp_kernel, repack_f32_kernel, mesh_diameter_kernel);
+  return e == cudaSuccess ? nullptr : "loading the preprocessing kernels failed (not an sm_100a device?)";
 }
 
 void launch_depth_to_xyz(const float* depth, float* xyz, int h, int w, const Intrinsics& K, cudaStream_t s) {
@@ -869,11 +1001,11 @@ void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float dia
   pose_setup_kernel<<<(n + 63) / 64, 64, 0, s>>>(poses, n, K, diameter, crop_ratio, aux);
 }
 
-int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr, __half* packed,
-                  int img0, int32_t* rast_id_debug, int* status, unsigned long long* zbuf_scratch, int zbuf_poses,
+int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vrec, __half* packed, int img0,
+                  int32_t* rast_id_debug, int* status, unsigned long long* zbuf_scratch, int zbuf_poses,
                   int num_sms, int split_mode, cudaStream_t s) {
   if (n <= 0) return 0;
-  vertex_stage_kernel<<<dim3((mesh.num_vertices + 255) / 256, n), 256, 0, s>>>(mesh, aux, vclip, vattr);
+  vertex_stage_kernel<<<dim3((mesh.num_vertices + 255) / 256, n), 256, 0, s>>>(mesh, aux, vrec);
   const int sms = num_sms > 0 ? num_sms : 148;
   // band kernel: 2 CTAs per hypothesis and 2 resident CTAs per SM; below ~2 CTAs per SM it is bound by the
   // latency of one CTA walking every triangle (N = 1 and N = 32 take the same ~105 us)
@@ -881,19 +1013,28 @@ int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vcl
   if (split_mode >= 0) split = split_mode != 0;  // tests run both paths on the same input
   if (split && zbuf_scratch && n <= zbuf_poses) {
     // few hypotheses: spread the triangles over the machine (see raster_split_kernel)
-    cudaMemsetAsync(zbuf_scratch, 0xFF, sizeof(unsigned long long) * (size_t)n * kCrop * kCrop, s);
+    // (a fill kernel rather than cudaMemsetAsync: see clear_status_kernel in session.cu)
+    fill_u64_kernel<<<4 * sms, 256, 0, s>>>(zbuf_scratch, (long long)n * kCrop * kCrop, ~0ull);
     const int want = (2 * sms + n - 1) / n, have = (mesh.num_faces + kRenderThreads - 1) / kRenderThreads;
     const int slices = want < have ? want : have;
-    raster_split_kernel<<<dim3(slices, n), kRenderThreads, 0, s>>>(mesh, vclip, zbuf_scratch, status);
+    raster_split_kernel<<<dim3(slices, n), kRenderThreads, 0, s>>>(mesh, vrec, zbuf_scratch, status);
     constexpr int kShadeRows = 8;
-    shade_split_kernel<<<dim3(kCrop / kShadeRows, n), kRenderThreads, 0, s>>>(mesh, aux, vclip, vattr, packed, img0,
+    shade_split_kernel<<<dim3(kCrop / kShadeRows, n), kRenderThreads, 0, s>>>(mesh, aux, vrec, packed, img0,
                                                                              rast_id_debug, zbuf_scratch, kShadeRows);
     return 3;
   }
   static const int experiment = getenv("FPB200_RENDER_EXPERIMENT") ? atoi(getenv("FPB200_RENDER_EXPERIMENT")) : 0;
   if (experiment == 3) return 1;
-  render_kernel<<<dim3(kRenderTiles, n), kBandThreads, kCrop * kTileRows * 8, s>>>(mesh, aux, vclip, vattr, packed,
-                                                                                      img0, rast_id_debug, status, experiment);
+  // more hypotheses than SMs: one 160-row band per CTA (each triangle is set up once; 1.7 waves of 252 CTAs);
+  // fewer: two 80-row bands, twice the CTAs
+  static const int force_bands = getenv("FPB200_RENDER_BANDS") ? atoi(getenv("FPB200_RENDER_BANDS")) : 0;
+  const int bands = force_bands ? force_bands : (n > sms ? 1 : 2);
+  if (bands == 1)
+    render_kernel<1024, kCrop><<<dim3(1, n), 1024, kCrop * kCrop * 8, s>>>(mesh, aux, vrec, packed, img0,
+                                                                           rast_id_debug, status, experiment);
+  else
+    render_kernel<512, kCrop / 2><<<dim3(2, n), 512, kCrop * (kCrop / 2) * 8, s>>>(mesh, aux, vrec, packed, img0,
+                                                                                   rast_id_debug, status, experiment);
   return 2;
 }
 

@@ -37,8 +37,8 @@ struct DeviceMesh {
   const float* vertices;   // [V,3] centred
   const float* normals;    // [V,3]
   const float* texcoords;  // [V,2] already (u, 1-v)
-  const int32_t* faces;    // [T,3]
-  const float* texture;    // [th,tw,3] f32 = u8 * (1/255)
+  const int4* faces;       // [T] (i0, i1, i2, unused): one 16-byte load per triangle
+  const float4* texture;   // [th,tw] texels (r, g, b, unused), f32 = u8 * (1/255): one 16-byte load per bilinear tap
   int num_vertices, num_faces, tex_h, tex_w;
   float diameter;
 };
@@ -63,14 +63,14 @@ void launch_fill_hypotheses(const float* grid, const float* center, float* poses
 void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float diameter,
                        float crop_ratio, PoseAux* aux, cudaStream_t s);
 // Vertex stage + rasterise + shade + flip + normalise + pack hypothesis i into packed image
-// `img0 + i`.  vclip / vattr: scratch of n * num_vertices float4 each.  zbuf_scratch (may be null):
+// `img0 + i`.  vrec: scratch of n * num_vertices records of 2 float4.  zbuf_scratch (may be null):
 // zbuf_poses * 160 * 160 keys; with n <= zbuf_poses and few enough hypotheses to leave SMs idle the
 // triangles are spread over the whole machine on global z-buffers (identical result).
 constexpr int kSplitRenderPoses = 80;
 // rast_id_debug (may be null: the product path passes null unless a test asked for the ids) receives the
 // visibility id map [n,160,160] (triangle + 1, 0 = empty; GL row order).  num_sms: SM count of the session's
 // device; split_mode: -1 automatic, 0 band kernel, 1 split kernels.  Returns the number of kernels launched.
-int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vclip, float4* vattr,
+int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vrec,
                    __half* packed, int img0, int32_t* rast_id_debug, int* status,
                    unsigned long long* zbuf_scratch, int zbuf_poses, int num_sms, int split_mode, cudaStream_t s);
 // Crop/warp the observed rgb + xyz, normalise, pack into packed image `img0 + i`.

