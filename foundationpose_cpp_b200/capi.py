@@ -111,3 +111,10 @@ def debug_cross_attention(qkv_ptr: int, out_ptr: int, n: int, repeat: int = 0) -
     check(lib().fpb200_debug_cross_attention(C.c_void_p(qkv_ptr), C.c_void_p(out_ptr), C.c_int(n), C.c_int(repeat),
                                              C.byref(ms)))
     return ms.value
+
+
+def debug_stem_conv(packed_ptr: int, n_img: int, weight_ptr: int, bias_ptr: int, out_ptr: int, repeat: int = 0) -> float:
+    ms = C.c_float(0)
+    check(lib().fpb200_debug_stem_conv(C.c_void_p(packed_ptr), C.c_int(n_img), C.c_void_p(weight_ptr), C.c_void_p(bias_ptr),
+                                       C.c_void_p(out_ptr), C.c_int(repeat), C.byref(ms)))
+    return ms.value

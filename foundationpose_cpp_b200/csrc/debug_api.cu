@@ -3,11 +3,13 @@
 #include <cuda_runtime.h>
 
 #include <stdexcept>
+#include <vector>
 
 #include "../../include/fpb200.h"
 #include "common.h"
 #include "conv_gemm.h"
 #include "encoder_block.h"
+#include "stem_conv.h"
 #include "net_ops.h"
 
 using namespace fpb;
@@ -161,4 +163,30 @@ extern "C" int fpb200_debug_encoder_block(const fpb200_encoder_desc* c, int repe
   EncoderBlockPlan plan;
   if (const char* e = build_encoder_block(d, &plan)) return fail(FPB200_ERR_INVALID, "%s", e);
   return timed_launches([&]() { FPB_CUDA(launch_encoder_block(plan, 0)); }, repeat, ms_out);
+}
+
+// Stem convolution alone: packed [n_img][160][164][8] fp16 (+ one pad row) -> phase-split [n_img][4][40][40][64] fp16.
+// weight: DEVICE pointer, file layout of `enc.stem.w` ([64][448], layouts.pack_stem7); bias: device [64] f32.
+extern "C" int fpb200_debug_stem_conv(const void* packed, int n_img, const void* weight, const float* bias, void* out,
+                                      int repeat, float* ms_out) {
+  try {
+    std::vector<__half> w_file(64 * 448), w_kernel(64 * 448);
+    FPB_CUDA(cudaMemcpy(w_file.data(), weight, w_file.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+    reorder_stem_weights(w_file.data(), w_kernel.data());
+    __half* w_dev = nullptr;
+    FPB_CUDA(cudaMalloc(&w_dev, w_kernel.size() * sizeof(__half)));
+    FPB_CUDA(cudaMemcpy(w_dev, w_kernel.data(), w_kernel.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    float bias_host[64];
+    FPB_CUDA(cudaMemcpy(bias_host, bias, sizeof(bias_host), cudaMemcpyDeviceToHost));
+    StemConvPlan plan;
+    const char* e = build_stem_conv(static_cast<const __half*>(packed), n_img, w_dev, bias_host, static_cast<__half*>(out), &plan);
+    int rc = FPB200_OK;
+    if (e) rc = fail(FPB200_ERR_INVALID, "%s", e);
+    else rc = timed_launches([&]() { FPB_CUDA(launch_stem_conv(plan, 0)); }, repeat, ms_out);
+    cudaDeviceSynchronize();
+    cudaFree(w_dev);
+    return rc;
+  } catch (const std::exception& ex) {
+    return fail(FPB200_ERR_CUDA, "%s", ex.what());
+  }
 }

@@ -9,6 +9,7 @@
 #include "common.h"
 #include "encoder_block.h"
 #include "net_ops.h"
+#include "stem_conv.h"
 
 namespace fpb {
 
@@ -121,11 +122,18 @@ Network::Network(NetKind kind, const std::string& weight_path, Arena* arena)
   if (const char* e = attention_init()) throw std::runtime_error(e);
   if (const char* e = net_ops_init()) throw std::runtime_error(e);
   if (const char* e = encoder_block_init()) throw std::runtime_error(e);
-  if (const char* e = encoder_block_init()) throw std::runtime_error(e);
+  if (const char* e = stem_conv_init()) throw std::runtime_error(e);
+  {
+    std::vector<__half> reordered(64 * 448);
+    reorder_stem_weights(w_->host_f16("enc.stem.w", 64, 448), reordered.data());
+    FPB_CUDA(cudaMalloc(&stem_w_, reordered.size() * sizeof(__half)));
+    FPB_CUDA(cudaMemcpy(stem_w_, reordered.data(), reordered.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
   flops_per_hyp_ = plan(1).flops;
 }
 
 Network::~Network() {
+  if (stem_w_) cudaFree(stem_w_);
   for (auto e : ev_pool_) cudaEventDestroy(e);
 }
 
@@ -152,7 +160,17 @@ void Network::add_backbone(Plan& p, int n) {
   Arena& A = *arena_;
   const WeightFile& W = *w_;
   const int n2 = 2 * n;
-  {  // stem: 7x7 s2, (6 -> 64), packed input -> phase-split 80x80x64
+  static const bool stem_as_gemm = getenv("FPB200_STEM_GEMM") != nullptr;  // A/B measurements only
+  if (!stem_as_gemm) {
+    // stem: 7x7 s2, (6 -> 64), packed input -> phase-split 80x80x64: direct tcgen05 convolution reading its A operand
+    // in place from the input patch (stem_conv.cu)
+    StemConvPlan sp;
+    if (const char* e = build_stem_conv(A.packed, n2, stem_w_, W.host_f32("enc.stem.b", 64), A.stem, &sp)) throw std::runtime_error(e);
+    p.flops += sp.flops;
+    p.steps.push_back([sp](cudaStream_t s) { FPB_CUDA(launch_stem_conv(sp, s)); });
+    p.gemm_flops.resize(p.steps.size(), 0.0);
+    p.gemm_flops.back() = sp.flops;  // timed with the tcgen05 GEMM family (fpb200_set_gemm_profile)
+  } else {  // the same layer through the general implicit-GEMM kernel: one 64-wide K slab per filter row
     ConvGemmDesc d;
     d.in = A.packed;
     d.n_img = n2; d.planes = 2; d.in_h = 80; d.in_w = 80; d.cin = 64;

@@ -33,6 +33,10 @@ class WeightFile {
     return static_cast<const float*>(get(name, 1, d0, d1).dev);
   }
   // the same tensor in the host copy of the file (plan builders read small vectors without touching the device)
+  const __half* host_f16(const std::string& name, int d0, int d1 = -1) const {
+    return reinterpret_cast<const __half*>(host_.data() + (static_cast<const uint8_t*>(get(name, 0, d0, d1).dev) -
+                                                            static_cast<const uint8_t*>(blob_)));
+  }
   const float* host_f32(const std::string& name, int d0, int d1 = -1) const {
     return reinterpret_cast<const float*>(host_.data() + (static_cast<const uint8_t*>(get(name, 1, d0, d1).dev) -
                                                            static_cast<const uint8_t*>(blob_)));
@@ -91,6 +95,7 @@ class Network {
   std::map<int, std::unique_ptr<Plan>> plans_;
   double flops_per_hyp_ = 0;
   bool profile_ = false;
+  __half* stem_w_ = nullptr;  // stem weights in the direct-convolution kernel's tap order (stem_conv.cu)
   std::vector<cudaEvent_t> ev_pool_;
   size_t ev_used_ = 0;
   std::vector<double> ev_flops_;

@@ -37,35 +37,60 @@ __global__ void depth_to_xyz_kernel(const float* __restrict__ depth, float* __re
 }
 
 // ------------------------------------------------------------------ sampler depth filters
-// foundationpose_sampling.cu:21-82 (radius 2, 1 mm, ratio 0.8, zfar 100).
-__global__ void erode_depth_kernel(const float* __restrict__ depth, float* __restrict__ out, int H,
-                                   int W) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  const int h = blockIdx.y * blockDim.y + threadIdx.y;
-  if (w >= W || h >= H) return;
-  const float d_ori = depth[h * W + w];
-  if (d_ori < 0.1f || d_ori >= kZFar) {
-    out[h * W + w] = 0.f;
-    return;
+// ErodeDepth (foundationpose_sampling.cu:21-82: radius 2, 1 mm, ratio 0.8, zfar 100) and BilateralFilterDepth
+// (:84-164: radius 2, sigmaD 2, sigmaR 1e5) as ONE kernel: a CTA stages its 32 x 8 tile of the depth image with a
+// 4-pixel halo in shared memory, erodes the 36 x 12 pixels the bilateral window of the tile can reach, and filters
+// from that - the eroded image never touches HBM unless a caller asks for it.  Per pixel the neighbours are visited
+// in the reference's order (columns outside, rows inside) and summed in that order, so both results are the same
+// floats the two separate kernels of the reference produce.  Block (0, 0) also resets the sampler's scan counters.
+constexpr int kFiltTX = 32, kFiltTY = 8;
+__device__ __forceinline__ bool depth_valid(float d) { return d >= 0.1f && d < kZFar; }
+__global__ void __launch_bounds__(kFiltTX * kFiltTY)
+depth_filter_kernel(const float* __restrict__ depth, float* __restrict__ eroded_out, float* __restrict__ filtered, int H,
+                    int W, int* __restrict__ meta) {
+  constexpr int DW = kFiltTX + 8, DH = kFiltTY + 8, EW = kFiltTX + 4, EH = kFiltTY + 4;
+  __shared__ float s_d[DH][DW];
+  __shared__ float s_e[EH][EW];
+  const int tid = threadIdx.y * kFiltTX + threadIdx.x;
+  const int x0 = blockIdx.x * kFiltTX, y0 = blockIdx.y * kFiltTY;
+  if (meta && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+    meta[0] = 0;
+    meta[1] = INT_MAX;
+    meta[2] = -1;
+    meta[3] = INT_MAX;
+    meta[4] = -1;
   }
-  float bad = 0.f, total = 0.f;
-  for (int u = w - 2; u <= w + 2; ++u) {
-    if (u < 0 || u >= W) continue;
-    for (int v = h - 2; v <= h + 2; ++v) {
-      if (v < 0 || v >= H) continue;
-      const float cur = depth[v * W + u];
-      total += 1.f;
-      if (cur < 0.1f || cur >= kZFar || fabsf(cur - d_ori) > 0.001f) bad += 1.f;
+  for (int i = tid; i < DW * DH; i += kFiltTX * kFiltTY) {
+    const int ly = i / DW, lx = i - ly * DW;
+    const int gx = x0 - 4 + lx, gy = y0 - 4 + ly;
+    s_d[ly][lx] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? depth[gy * W + gx] : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < EW * EH; i += kFiltTX * kFiltTY) {
+    const int ly = i / EW, lx = i - ly * EW;
+    const int w = x0 - 2 + lx, h = y0 - 2 + ly;  // image coordinates of this eroded pixel
+    float e = 0.f;
+    if (w >= 0 && w < W && h >= 0 && h < H) {
+      const float d_ori = s_d[ly + 2][lx + 2];
+      if (depth_valid(d_ori)) {
+        float bad = 0.f, total = 0.f;
+        for (int u = w - 2; u <= w + 2; ++u) {
+          if (u < 0 || u >= W) continue;
+          for (int v = h - 2; v <= h + 2; ++v) {
+            if (v < 0 || v >= H) continue;
+            const float cur = s_d[v - y0 + 4][u - x0 + 4];
+            total += 1.f;
+            if (!depth_valid(cur) || fabsf(cur - d_ori) > 0.001f) bad += 1.f;
+          }
+        }
+        e = (bad / total) > 0.8f ? 0.f : d_ori;
+      }
+      if (eroded_out && lx >= 2 && lx < EW - 2 && ly >= 2 && ly < EH - 2) eroded_out[h * W + w] = e;
     }
+    s_e[ly][lx] = e;
   }
-  out[h * W + w] = (bad / total) > 0.8f ? 0.f : d_ori;
-}
-
-// foundationpose_sampling.cu:84-164 (radius 2, sigmaD 2, sigmaR 1e5).
-__global__ void bilateral_depth_kernel(const float* __restrict__ depth, float* __restrict__ out,
-                                       int H, int W) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  const int h = blockIdx.y * blockDim.y + threadIdx.y;
+  __syncthreads();
+  const int w = x0 + threadIdx.x, h = y0 + threadIdx.y;
   if (w >= W || h >= H) return;
   float mean = 0.f;
   int num_valid = 0;
@@ -73,27 +98,27 @@ __global__ void bilateral_depth_kernel(const float* __restrict__ depth, float* _
     if (u < 0 || u >= W) continue;
     for (int v = h - 2; v <= h + 2; ++v) {
       if (v < 0 || v >= H) continue;
-      const float cur = depth[v * W + u];
-      if (cur >= 0.1f && cur < kZFar) {
+      const float cur = s_e[v - y0 + 2][u - x0 + 2];
+      if (depth_valid(cur)) {
         ++num_valid;
         mean += cur;
       }
     }
   }
   if (num_valid == 0) {
-    out[h * W + w] = 0.f;
+    filtered[h * W + w] = 0.f;
     return;
   }
   mean /= (float)num_valid;
-  const float center = depth[h * W + w];
+  const float center = s_e[threadIdx.y + 2][threadIdx.x + 2];
   float sum_w = 0.f, sum = 0.f;
   const float sigma_d = 2.f, sigma_r = 100000.f;
   for (int u = w - 2; u <= w + 2; ++u) {
     if (u < 0 || u >= W) continue;
     for (int v = h - 2; v <= h + 2; ++v) {
       if (v < 0 || v >= H) continue;
-      const float cur = depth[v * W + u];
-      if (cur >= 0.1f && cur < kZFar && fabsf(cur - mean) < 0.01f) {
+      const float cur = s_e[v - y0 + 2][u - x0 + 2];
+      if (depth_valid(cur) && fabsf(cur - mean) < 0.01f) {
         const float wgt = expf(-((float)((u - w) * (u - w) + (v - h) * (v - h))) / (2.f * sigma_d * sigma_d) -
                                (center - cur) * (center - cur) / (2.f * sigma_r * sigma_r));
         sum_w += wgt;
@@ -101,7 +126,7 @@ __global__ void bilateral_depth_kernel(const float* __restrict__ depth, float* _
       }
     }
   }
-  out[h * W + w] = (sum_w > 0.f) ? sum / sum_w : 0.f;
+  filtered[h * W + w] = (sum_w > 0.f) ? sum / sum_w : 0.f;
 }
 
 // ------------------------------------------------------------------ translation guess
@@ -111,16 +136,6 @@ __global__ void bilateral_depth_kernel(const float* __restrict__ depth, float* _
 //  (2) median_select_kernel (one CTA): exact median of the list by 4-pass radix select on the float
 //      bit patterns (depths are positive, so the patterns order like the values; the reference uses
 //      std::sort), then K^-1 back-projection.  meta = {count, umin, umax, vmin, vmax}.
-__global__ void sampler_init_kernel(int* __restrict__ meta) {
-  if (threadIdx.x == 0) {
-    meta[0] = 0;
-    meta[1] = INT_MAX;
-    meta[2] = -1;
-    meta[3] = INT_MAX;
-    meta[4] = -1;
-  }
-}
-
 __global__ void mask_scan_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ mask, int h, int w,
                                  unsigned* __restrict__ list, int* __restrict__ meta) {
   const int npx = h * w;
@@ -164,9 +179,11 @@ __global__ void mask_scan_kernel(const float* __restrict__ depth, const uint8_t*
 
 __global__ void __launch_bounds__(1024, 1)
 median_select_kernel(const unsigned* __restrict__ list, const int* __restrict__ meta, Intrinsics K,
-                     float* __restrict__ center, int* __restrict__ status) {
+                     float* __restrict__ center, int* __restrict__ status, const float* __restrict__ grid,
+                     float* __restrict__ poses, int n_poses) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_rank, s_cnt_less, s_max_less;
+  __shared__ float s_center[3];
   const int tid = threadIdx.x;
   if (meta[2] < 0) {
     if (tid == 0) atomicOr(status, kStatusEmptyMask);
@@ -193,14 +210,31 @@ median_select_kernel(const unsigned* __restrict__ list, const int* __restrict__ 
       if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
-      unsigned r = s_rank, b = 0;
-      for (; b < 256; ++b) {
-        if (r < hist[b]) break;
-        r -= hist[b];
+    if (tid < 32) {
+      // bucket holding rank r: warp scan over 32 groups of 8 bins instead of a serial walk over 256 bins
+      unsigned bins[8], group = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bins[j] = hist[tid * 8 + j];
+        group += bins[j];
       }
-      s_rank = r;
-      s_prefix = prefix | (b << shift);
+      unsigned incl = group;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      const unsigned r = s_rank, before = incl - group;
+      if (r >= before && r < incl) {  // exactly one lane (total counts of this pass exceed r)
+        unsigned rr = r - before;
+        int j = 0;
+        for (; j < 7; ++j) {
+          if (rr < bins[j]) break;
+          rr -= bins[j];
+        }
+        s_rank = rr;
+        s_prefix = prefix | ((unsigned)(tid * 8 + j) << shift);
+      }
     }
     __syncthreads();
   }
@@ -213,8 +247,15 @@ median_select_kernel(const unsigned* __restrict__ list, const int* __restrict__ 
       max_less = max(max_less, key);
     }
   }
-  atomicAdd(&s_cnt_less, cnt_less);
-  atomicMax(&s_max_less, max_less);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt_less += __shfl_xor_sync(0xffffffffu, cnt_less, o);
+    max_less = max(max_less, __shfl_xor_sync(0xffffffffu, max_less, o));
+  }
+  if ((tid & 31) == 0) {
+    atomicAdd(&s_cnt_less, cnt_less);
+    atomicMax(&s_max_less, max_less);
+  }
   __syncthreads();
   if (tid == 0) {
     const float hi = __uint_as_float(hi_key);
@@ -225,20 +266,18 @@ median_select_kernel(const unsigned* __restrict__ list, const int* __restrict__ 
     }
     const float uc = (float)(meta[1] + meta[2]) / 2.f;
     const float vc = (float)(meta[3] + meta[4]) / 2.f;
-    for (int r = 0; r < 3; ++r)
-      center[r] = ((K.kinv[3 * r] * uc + K.kinv[3 * r + 1] * vc) + K.kinv[3 * r + 2]) * zc;
+    for (int r = 0; r < 3; ++r) {
+      s_center[r] = ((K.kinv[3 * r] * uc + K.kinv[3 * r + 1] * vc) + K.kinv[3 * r + 2]) * zc;
+      center[r] = s_center[r];
+    }
   }
-}
-
-// GetHypPoses step 4, foundationpose_sampling.cpp:388-391.
-__global__ void fill_hypotheses_kernel(const float* __restrict__ grid, const float* __restrict__ center,
-                                       float* __restrict__ poses, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * 16) return;
-  const int e = i & 15;
-  float v = grid[i];
-  if (e >= 12 && e < 15) v = center[e - 12];
-  poses[i] = v;
+  __syncthreads();
+  // GetHypPoses step 4, foundationpose_sampling.cpp:388-391: every rotation of the grid at the guessed translation
+  if (poses)
+    for (int i = tid; i < n_poses * 16; i += blockDim.x) {
+      const int e = i & 15;
+      poses[i] = (e >= 12 && e < 15) ? s_center[e - 12] : grid[i];
+    }
 }
 
 // ------------------------------------------------------------------ per-pose setup
@@ -964,8 +1003,8 @@ const char* preprocess_init() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(render_kernel<1024, kCrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrop * kCrop * 8);
   if (e != cudaSuccess) return "cudaFuncSetAttribute(render_kernel smem) failed";
-  e = preload_kernels(depth_to_xyz_kernel, erode_depth_kernel, bilateral_depth_kernel, sampler_init_kernel, mask_scan_kernel,
-                      median_select_kernel, fill_hypotheses_kernel, pose_setup_kernel, vertex_stage_kernel, fill_u64_kernel,
+  e = preload_kernels(depth_to_xyz_kernel, depth_filter_kernel, mask_scan_kernel,
+                      median_select_kernel, pose_setup_kernel, vertex_stage_kernel, fill_u64_kernel,
                       raster_split_kernel, shade_split_kernel, warp_kernel, repack_f32_kernel, mesh_diameter_kernel);
   return e == cudaSuccess ? nullptr : "loading the preprocessing kernels failed (not an sm_100a device?)";
 }
@@ -975,25 +1014,21 @@ void launch_depth_to_xyz(const float* depth, float* xyz, int h, int w, const Int
   depth_to_xyz_kernel<<<(n + 255) / 256, 256, 0, s>>>(depth, xyz, h, w, K.fx, K.fy, K.cx, K.cy);
 }
 
-void launch_depth_filters(const float* depth, float* eroded, float* filtered, int h, int w, cudaStream_t s) {
-  dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-  erode_depth_kernel<<<grid, block, 0, s>>>(depth, eroded, h, w);
-  bilateral_depth_kernel<<<grid, block, 0, s>>>(eroded, filtered, h, w);
+void launch_depth_filters(const float* depth, float* eroded, float* filtered, int h, int w, int* sampler_meta,
+                          cudaStream_t s) {
+  dim3 block(kFiltTX, kFiltTY), grid((w + kFiltTX - 1) / kFiltTX, (h + kFiltTY - 1) / kFiltTY);
+  depth_filter_kernel<<<grid, block, 0, s>>>(depth, eroded, filtered, h, w, sampler_meta);
 }
 
 void launch_guess_translation(const float* filtered, const uint8_t* mask, int h, int w, const Intrinsics& K,
-                              float* center, int* status, unsigned* scratch, cudaStream_t s) {
-  // scratch: [8] ints of meta followed by h*w list entries
+                              float* center, int* status, unsigned* scratch, const float* grid, float* poses,
+                              int n_poses, cudaStream_t s) {
+  // scratch: [8] ints of meta (reset by launch_depth_filters) followed by h*w list entries
   int* meta = reinterpret_cast<int*>(scratch);
   unsigned* list = scratch + 8;
-  sampler_init_kernel<<<1, 32, 0, s>>>(meta);
   const int blocks = (h * w + 1023) / 1024;
   mask_scan_kernel<<<blocks, 256, 0, s>>>(filtered, mask, h, w, list, meta);
-  median_select_kernel<<<1, 1024, 0, s>>>(list, meta, K, center, status);
-}
-
-void launch_fill_hypotheses(const float* grid, const float* center, float* poses, int n, cudaStream_t s) {
-  fill_hypotheses_kernel<<<(n * 16 + 255) / 256, 256, 0, s>>>(grid, center, poses, n);
+  median_select_kernel<<<1, 1024, 0, s>>>(list, meta, K, center, status, grid, poses, n_poses);
 }
 
 void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float diameter, float crop_ratio,

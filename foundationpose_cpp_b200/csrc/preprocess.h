@@ -50,16 +50,16 @@ constexpr int kStatusClipPath = 4;  // informational: some triangle took cudaras
 
 void launch_depth_to_xyz(const float* depth, float* xyz, int h, int w, const Intrinsics& K,
                          cudaStream_t s);
-void launch_depth_filters(const float* depth, float* eroded, float* filtered, int h, int w,
+// Erode + bilateral filter of the depth image in one kernel.  eroded may be null (the intermediate image is only
+// stored on request); sampler_meta (may be null): the 8-int header of the guess-translation scratch, reset here.
+void launch_depth_filters(const float* depth, float* eroded, float* filtered, int h, int w, int* sampler_meta,
                           cudaStream_t s);
-// Mask bounding box + median depth + K^-1 back-projection; writes center[3] and status.
-// scratch: 8 + h*w 32-bit words.
+// Mask bounding box + median depth + K^-1 back-projection; writes center[3] and status, and (poses != null) the
+// n_poses hypotheses = rotation grid at that translation (col-major 4x4).  scratch: 8 + h*w 32-bit words whose
+// header launch_depth_filters has reset.
 void launch_guess_translation(const float* filtered, const uint8_t* mask, int h, int w,
-                              const Intrinsics& K, float* center, int* status, unsigned* scratch,
-                              cudaStream_t s);
-// poses[i] = grid[i] with translation = center (col-major 4x4).
-void launch_fill_hypotheses(const float* grid, const float* center, float* poses, int n,
-                            cudaStream_t s);
+                              const Intrinsics& K, float* center, int* status, unsigned* scratch, const float* grid,
+                              float* poses, int n_poses, cudaStream_t s);
 void launch_pose_setup(const float* poses, int n, const Intrinsics& K, float diameter,
                        float crop_ratio, PoseAux* aux, cudaStream_t s);
 // Vertex stage + rasterise + shade + flip + normalise + pack hypothesis i into packed image

@@ -265,7 +265,7 @@ struct fpb200_session {
   std::vector<std::unique_ptr<MeshEntry>> meshes;
   MeshEntry* cur_mesh = nullptr;
   DevBuf<uint8_t> rgb, mask;
-  DevBuf<float> depth, xyz, eroded, filtered, grid, poses, center, exch_local, exch_all, feats, tail_qkv,
+  DevBuf<float> depth, xyz, filtered, grid, poses, center, exch_local, exch_all, feats, tail_qkv,
       tail_att, tail_out, scores, trans, rot, best_pose, all_poses;
   DevBuf<int> status, best_index;
   DevBuf<unsigned> sampler_scratch;
@@ -401,12 +401,13 @@ void do_mask_copy(fpb200_session* s, const uint8_t* mask) {
 void do_sample(fpb200_session* s, MeshEntry* mesh) {
   FPB_NVTX("fpb200/sample_hypotheses");
   const int h = s->img_h, w = s->img_w;
-  launch_depth_filters(s->depth.p, s->eroded.p, s->filtered.p, h, w, s->stream);
-  launch_guess_translation(s->filtered.p, s->mask.p, h, w, s->intr, s->center.p, s->status.p, s->sampler_scratch.p,
-                           s->stream);
+  // one filter kernel (erode + bilateral; the eroded image stays on chip), one scan, one select that also writes
+  // the hypotheses
   const int n = std::min(kGridPoses, s->opt.max_hyps);
-  launch_fill_hypotheses(s->grid.p, s->center.p, s->poses.p, n, s->stream);
-  s->count_launches(6);
+  launch_depth_filters(s->depth.p, nullptr, s->filtered.p, h, w, reinterpret_cast<int*>(s->sampler_scratch.p), s->stream);
+  launch_guess_translation(s->filtered.p, s->mask.p, h, w, s->intr, s->center.p, s->status.p, s->sampler_scratch.p,
+                           s->grid.p, s->poses.p, n, s->stream);
+  s->count_launches(3);
   s->cur_mesh = mesh;
   s->set_shard(n);
   s->mark(2);
@@ -719,7 +720,7 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
     const size_t px = (size_t)max_h * max_w;
     const int cap = s->opt.max_hyps;
     s->rgb.alloc(px * 3); s->mask.alloc(px); s->depth.alloc(px); s->xyz.alloc(px * 3);
-    s->eroded.alloc(px); s->filtered.alloc(px); s->sampler_scratch.alloc(px + 8);
+    s->filtered.alloc(px); s->sampler_scratch.alloc(px + 8);
     const std::vector<float> grid = make_rotation_grid();
     s->grid.upload(grid.data(), grid.size());
     s->poses.alloc((size_t)cap * 16); s->all_poses.alloc((size_t)cap * 16);

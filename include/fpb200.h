@@ -260,6 +260,11 @@ typedef struct {
 } fpb200_encoder_desc;
 int fpb200_debug_encoder_block(const fpb200_encoder_desc* desc, int repeat, float* ms_out);
 
+/* Stem convolution alone (7 x 7, stride 2, 6 -> 64; csrc/stem_conv.cu): packed [n_img][160][164][8] fp16 (+ one pad row)
+ * -> phase-split [n_img][4][40][40][64] fp16 with bias + ReLU.  weight: file layout of `enc.stem.w` ([64][448] fp16). */
+int fpb200_debug_stem_conv(const void* packed, int n_img, const void* weight, const float* bias, void* out, int repeat,
+                           float* ms_out);
+
 /* fp32 operators of the scorer tail (after the token mean; inside the scorer engine in the reference):
  * out[rows, outs] = in[rows, k] w[outs, k]^T + b (b may be NULL), and the cross-hypothesis attention
  * qkv [n, 1536] (Q | K | V, 4 heads x 128) -> out [n, 512].  Once + `repeat` timed launches. */

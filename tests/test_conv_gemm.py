@@ -143,6 +143,25 @@ def test_stem7_and_phase_split_out(cluster):
     _check(layouts.phase_merge(out), ref, f"stem 7x7 s2 cl{cluster}")
 
 
+@pytest.mark.parametrize("n", [1, 3, 37])
+def test_stem_direct_convolution(n):
+    """csrc/stem_conv.cu: the stem as a direct tcgen05 convolution whose A operand is read in place from the
+    parity-split input patch (no-swizzle K-major descriptors, two filter taps per MMA).  Against F.conv2d fp32 on the
+    same fp16 operands; every output of every tile position (image borders = TMA out-of-bounds zero fill), 1 image
+    (50 tiles, fewer CTAs than SMs), 3 and 37 images (1 850 tiles on 296 persistent CTAs: ring wrap-around)."""
+    torch.manual_seed(30 + n)
+    x = _rand(n, 160, 160, 6)
+    buf = layouts.pad_stem_input(x)
+    w = _rand(64, 6, 7, 7, scale=(49 * 6) ** -0.5)
+    b = torch.randn(64, device="cuda")
+    out = torch.full((n, 4, 40, 40, 64), float("nan"), device="cuda", dtype=torch.float16)
+    wf = layouts.pack_stem7(w).contiguous()
+    capi.debug_stem_conv(buf.data_ptr(), n, wf.data_ptr(), b.data_ptr(), out.data_ptr())
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=2, padding=3).permute(0, 2, 3, 1).relu()
+    _check(layouts.phase_merge(out), ref, f"stem direct conv n{n}")
+
+
 def test_concat_halves(cluster, block_n):
     """Images n >= img_mod land in the same pixel at a channel offset (a||b feature concat)."""
     _bn_ok(block_n, 128)
