@@ -164,11 +164,18 @@ token_mean_kernel(const __half* __restrict__ x, float* __restrict__ out) {
   const int n = blockIdx.x, grp = threadIdx.x >> 8, t256 = threadIdx.x & 255;
   const __half2* p = reinterpret_cast<const __half2*>(x + (static_cast<long long>(n) * kTok + grp * 100) * kDim) + t256;
   float sx = 0.f, sy = 0.f;
-#pragma unroll 4
-  for (int t = 0; t < 100; ++t) {
-    const float2 f = __half22float2(p[static_cast<long long>(t) * (kDim / 2)]);
-    sx += f.x;
-    sy += f.y;
+  // 25 independent row loads in flight per thread (the sums stay in token order): with one CTA per hypothesis the
+  // kernel is a chain of memory round trips, 4 batches instead of 25
+  for (int t0 = 0; t0 < 100; t0 += 25) {
+    __half2 v[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) v[t] = p[static_cast<long long>(t0 + t) * (kDim / 2)];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) {
+      const float2 f = __half22float2(v[t]);
+      sx += f.x;
+      sy += f.y;
+    }
   }
   part[grp][t256] = make_float2(sx, sy);
   __syncthreads();

@@ -225,6 +225,7 @@ median_select_kernel(const unsigned* __restrict__ list, const int* __restrict__ 
         if (tid >= o) incl += v;
       }
       const unsigned r = s_rank, before = incl - group;
+      __syncwarp();  // every lane has read s_rank before the owning lane overwrites it (racecheck: read / write hazard)
       if (r >= before && r < incl) {  // exactly one lane (total counts of this pass exceed r)
         unsigned rr = r - before;
         int j = 0;
@@ -1050,12 +1051,15 @@ int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vre
     // few hypotheses: spread the triangles over the machine (see raster_split_kernel)
     // (a fill kernel rather than cudaMemsetAsync: see clear_status_kernel in session.cu)
     fill_u64_kernel<<<4 * sms, 256, 0, s>>>(zbuf_scratch, (long long)n * kCrop * kCrop, ~0ull);
-    const int want = (2 * sms + n - 1) / n, have = (mesh.num_faces + kRenderThreads - 1) / kRenderThreads;
-    const int slices = want < have ? want : have;
+    // one or two triangles per thread: the kernel is a chain of dependent gathers, so its duration is the number of
+    // triangles a thread walks (FPB200_SPLIT_SLICES: measurements only)
+    static const int force_slices = getenv("FPB200_SPLIT_SLICES") ? atoi(getenv("FPB200_SPLIT_SLICES")) : 0;
+    const int want = (32 * sms + n - 1) / n, have = (mesh.num_faces + kRenderThreads - 1) / kRenderThreads;
+    const int slices = force_slices ? (force_slices < have ? force_slices : have) : (want < have ? want : have);
     raster_split_kernel<<<dim3(slices, n), kRenderThreads, 0, s>>>(mesh, vrec, zbuf_scratch, status);
-    constexpr int kShadeRows = 8;
-    shade_split_kernel<<<dim3(kCrop / kShadeRows, n), kRenderThreads, 0, s>>>(mesh, aux, vrec, packed, img0,
-                                                                             rast_id_debug, zbuf_scratch, kShadeRows);
+    static const int shade_rows = getenv("FPB200_SPLIT_SHADE_ROWS") ? atoi(getenv("FPB200_SPLIT_SHADE_ROWS")) : 2;
+    shade_split_kernel<<<dim3(kCrop / shade_rows, n), kRenderThreads, 0, s>>>(mesh, aux, vrec, packed, img0,
+                                                                             rast_id_debug, zbuf_scratch, shade_rows);
     return 3;
   }
   static const int experiment = getenv("FPB200_RENDER_EXPERIMENT") ? atoi(getenv("FPB200_RENDER_EXPERIMENT")) : 0;
