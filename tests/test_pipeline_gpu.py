@@ -333,3 +333,103 @@ def test_mesh_diameter_on_device_matches_all_pairs_maximum(tmp_path):
     finally:
         m0.close()
         m1.close()
+
+
+def test_two_meshes_in_one_session_match_single_mesh_sessions(tmp_path):
+    """one session holding two meshes (map_name2renderer_ of the reference,
+    foundationpose.cpp:141-151).  Register of either target - alternating, so the per-mesh CUDA graphs and the shared
+    vertex scratch are reused across targets - must give exactly what a session holding only that mesh gives."""
+    rp, sp = helpers.write_seeded_weights(str(tmp_path))
+    mesh_a = synth.uv_ellipsoid("a", slices=48, stacks=25, tex_size=128, seed=0)
+    mesh_b = synth.uv_ellipsoid("b", slices=64, stacks=33, axes=(0.07, 0.05, 0.06), tex_size=64, seed=5)
+    scene_a = synth.make_scene(mesh_a)
+    scene_b = synth.make_scene(mesh_b, t=(-0.03, 0.02, 0.7), rot_seed=4)
+    want = {}
+    for mesh, scene in ((mesh_a, scene_a), (mesh_b, scene_b)):
+        m1 = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], synth.DEFAULT_K, max_h=480,
+                                           max_w=640, max_hyps=40)
+        ok, pose = m1.Register(scene[0], scene[1], scene[2], mesh.name, refine_itr=1)
+        assert ok, m1.last_error
+        want[mesh.name] = (pose, m1.read_buffer("scores", np.float32, 40).copy())
+        m1.close()
+    both = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh_a),
+                                                  api.ArrayMeshLoader.from_mesh_data(mesh_b)], synth.DEFAULT_K,
+                                         max_h=480, max_w=640, max_hyps=40)
+    try:
+        for name, scene in (("a", scene_a), ("b", scene_b), ("a", scene_a), ("b", scene_b), ("b", scene_b), ("a", scene_a)):
+            ok, pose = both.Register(scene[0], scene[1], scene[2], name, refine_itr=1)
+            assert ok, both.last_error
+            assert np.array_equal(pose, want[name][0]), name
+            assert np.array_equal(both.read_buffer("scores", np.float32, 40), want[name][1]), name
+        ok, _ = both.Register(scene_a[0], scene_a[1], scene_a[2], "c", refine_itr=1)
+        assert not ok and "unknown target" in both.last_error
+    finally:
+        both.close()
+
+
+def test_skewed_intrinsics_match_oracle(tmp_path):
+    """K[0][1] != 0: the crop-window projection and the GL projection matrix use the full K
+    (foundationpose_render.cpp:44-75,151-186) while depth -> xyz ignores the skew like the reference kernel
+    (foundationpose_utils.cu:3-32).  Sampler, crop transform, visibility ids and packed inputs against the oracle."""
+    rp, sp = helpers.write_seeded_weights(str(tmp_path))
+    K = synth.DEFAULT_K.copy()
+    K[0, 1] = 2.5
+    mesh = synth.uv_ellipsoid("obj", slices=48, stacks=25, tex_size=128, seed=2)
+    rgb, depth, mask, gt = synth.make_scene(mesh, K=K)
+    m = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], K, max_h=480, max_w=640, max_hyps=252)
+    try:
+        m.debug_options(rast_ids=True)
+        m.upload(rgb, depth)
+        m.sample_hypotheses(mask, "obj")
+        got = m.get_hypotheses()
+        ref = O.sample_hypotheses(depth, mask, K)
+        np.testing.assert_allclose(got[:, :3, 3], ref[:, :3, 3], rtol=2e-6, atol=1e-7)
+        assert abs(ref[0, 0, 3] - O.sample_hypotheses(depth, mask, synth.DEFAULT_K)[0, 0, 3]) > 1e-6  # the skew matters
+        poses = np.concatenate([ref[[3, 77, 160]], gt[None]], 0)
+        m.set_hypotheses(poses, "obj")
+        m.render_and_transform(1.2)
+        n = len(poses)
+        ren, tra, info = O.render_and_transform(helpers.oracle_mesh(mesh), poses, rgb, O.depth_to_xyz(depth, K), K, 1.2)
+        np.testing.assert_array_equal(m.read_buffer("crop_tf", np.float32, n * 9).reshape(n, 3, 3), info["tf"].astype(F))
+        ids = m.read_buffer("rast_id", np.int32, n * 160 * 160).reshape(n, 160, 160)
+        assert np.array_equal(ids, info["ids"]), f"{int((ids != info['ids']).sum())} visibility ids differ"
+        _fp16_close(m.read_packed("transf_input", n), tra, "transf_input (skewed K)")
+        _fp16_close(m.read_packed("render_input", n), ren, "render_input (skewed K)")
+    finally:
+        m.close()
+
+
+def test_full_hd_frame_with_default_capacity(tmp_path):
+    """1080 x 1920 frames, the reference's default max_input_image_height / width (foundationpose.hpp:99-105): the
+    session is created with the defaults; sampler (whole-image depth filters, mask scan, median) and the packed network
+    inputs against the oracle, then Register / Track through the public call."""
+    rp, sp = helpers.write_seeded_weights(str(tmp_path))
+    K = np.array([[1400.0, 0, 960.0], [0, 1400.0, 540.0], [0, 0, 1]], F)
+    mesh = synth.uv_ellipsoid("obj", slices=48, stacks=25, tex_size=128, seed=1)
+    rgb, depth, mask, gt = synth.make_scene(mesh, K=K, h=1080, w=1920, t=(0.15, -0.08, 0.55))
+    m = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(mesh)], K, max_hyps=252)
+    try:
+        m.debug_options(rast_ids=True)
+        m.upload(rgb, depth)
+        m.sample_hypotheses(mask, "obj")
+        ref = O.sample_hypotheses(depth, mask, K)
+        np.testing.assert_allclose(m.get_hypotheses()[:, :3, 3], ref[:, :3, 3], rtol=2e-6, atol=1e-7)
+        poses = np.concatenate([ref[[10, 200]], gt[None]], 0)
+        m.set_hypotheses(poses, "obj")
+        m.render_and_transform(1.2)
+        ren, tra, info = O.render_and_transform(helpers.oracle_mesh(mesh), poses, rgb, O.depth_to_xyz(depth, K), K, 1.2)
+        ids = m.read_buffer("rast_id", np.int32, 3 * 160 * 160).reshape(3, 160, 160)
+        assert np.array_equal(ids, info["ids"])
+        _fp16_close(m.read_packed("transf_input", 3), tra, "transf_input (1080p)")
+        _fp16_close(m.read_packed("render_input", 3), ren, "render_input (1080p)")
+        m.debug_options()
+        ok, pose = m.Register(rgb, depth, mask, "obj", refine_itr=1)
+        assert ok and np.isfinite(pose).all(), m.last_error
+        ok, pose2 = m.Track(rgb, depth, gt, "obj", refine_itr=2)
+        assert ok and np.isfinite(pose2).all(), m.last_error
+        # a frame larger than the capacity is refused, not truncated
+        big = np.zeros((1081, 1920, 3), np.uint8)
+        ok, _ = m.Track(big, np.zeros((1081, 1920), F), gt, "obj")
+        assert not ok
+    finally:
+        m.close()
