@@ -642,7 +642,7 @@ def main():
                 "d2h_bytes_per_step": 72, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: all 15 conv layers + the QKV projections)",
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel + stem_conv_kernel (tcgen05 implicit GEMM family: the 15 conv layers + the QKV projections)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src, "launches_timed": int(gemm_launches),
                      "kernel_ms_per_step": gemm_ms / args.steps, "kernel_share_of_step": gemm_ms / prof_ms if prof_ms else None,

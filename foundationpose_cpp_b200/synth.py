@@ -135,7 +135,7 @@ def make_scene(mesh: MeshData, K=DEFAULT_K, h: int = 480, w: int = 640, t=(0.02,
     diffuse = np.clip(-n_cam[..., 2], 0, 1)
     col_obj = np.clip(tex * (0.8 + 0.5 * diffuse[..., None]), 0, 1)
     rng = np.random.default_rng(noise_seed)
-    bg = np.kron(rng.random((h // 16, w // 16, 3)), np.ones((16, 16, 1))) * 0.6 + 0.2
+    bg = (np.kron(rng.random((-(-h // 16), -(-w // 16), 3)), np.ones((16, 16, 1))) * 0.6 + 0.2)[:h, :w]
     rgb = np.where(hit[..., None], col_obj, bg)
     depth = np.where(hit, lam, background_z).astype(np.float64)  # rays have z = 1 -> lam is depth
     depth += rng.normal(0, 0.001, depth.shape)
