@@ -79,13 +79,12 @@ Arena::Arena(int max_hyps) : cap(max_hyps) {
   const size_t n = (size_t)max_hyps;
   struct Item { void** p; size_t bytes; };
   const size_t tok = n * 400 * 512 * 2;
+  const size_t stem_out = 2 * n * 80 * 80 * 64 * 2;
+  act_bytes = stem_out;
   std::vector<Item> items = {
       {(void**)&packed, (2 * n * (size_t)kPackImageElems + (size_t)kStemPitch * kPackC) * 2},
-      {(void**)&stem, 2 * n * 80 * 80 * 64 * 2},
-      {(void**)&a0, 2 * n * 40 * 40 * 128 * 2}, {(void**)&a1, 2 * n * 40 * 40 * 128 * 2},
-      {(void**)&a2, 2 * n * 40 * 40 * 128 * 2},
-      {(void**)&c0, n * 40 * 40 * 256 * 2}, {(void**)&c1, n * 40 * 40 * 256 * 2}, {(void**)&c2, n * 40 * 40 * 256 * 2},
-      {(void**)&d0, tok}, {(void**)&d1, tok}, {(void**)&d2, tok},
+      {(void**)&act[0], stem_out}, {(void**)&act[1], stem_out}, {(void**)&act[2], stem_out}, {(void**)&act[3], stem_out},
+      {(void**)&d0, tok},
       {(void**)&qkv, 3 * tok}, {(void**)&att, tok}, {(void**)&proj, tok}, {(void**)&x1, tok},
       {(void**)&ff1, tok}, {(void**)&ff2, tok}, {(void**)&x2, tok},
       {(void**)&mean_t, n * 512 * 4}, {(void**)&mean_r, n * 512 * 4},
@@ -124,8 +123,21 @@ Network::Network(NetKind kind, const std::string& weight_path, Arena* arena)
   if (const char* e = encoder_block_init()) throw std::runtime_error(e);
   if (const char* e = stem_conv_init()) throw std::runtime_error(e);
   {
+    // the backbone's layer list is data: "arch" f32 [L, 4] rows (section, kind, cout, stride)
+    const WeightTensor* a = w_->find("arch");
+    if (!a || a->dtype != 1 || a->ndim != 2 || a->dims[1] != 4 || a->dims[0] < 2 || a->dims[0] > 64)
+      throw std::runtime_error("weight file " + weight_path + " carries no valid 'arch' table (re-export it with "
+                               "foundationpose_cpp_b200/weights.py)");
+    const float* v = static_cast<const float*>(w_->host_ptr(*a));
+    for (int i = 0; i < a->dims[0]; ++i)
+      arch_.push_back(ArchLayer{(int)v[4 * i], (int)v[4 * i + 1], (int)v[4 * i + 2], (int)v[4 * i + 3]});
+    const ArchLayer& s0 = arch_[0];
+    if (s0.sec != 0 || s0.kind != 0 || s0.cout != 64 || s0.stride != 2)
+      throw std::runtime_error("arch: the first layer must be the 7x7 stride-2 stem with 64 outputs");
+  }
+  {
     std::vector<__half> reordered(64 * 448);
-    reorder_stem_weights(w_->host_f16("enc.stem.w", 64, 448), reordered.data());
+    reorder_stem_weights(w_->host_f16("enc.A.0.w", 64, 448), reordered.data());
     FPB_CUDA(cudaMalloc(&stem_w_, reordered.size() * sizeof(__half)));
     FPB_CUDA(cudaMemcpy(stem_w_, reordered.data(), reordered.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
@@ -160,31 +172,6 @@ void Network::add_backbone(Plan& p, int n) {
   Arena& A = *arena_;
   const WeightFile& W = *w_;
   const int n2 = 2 * n;
-  static const bool stem_as_gemm = getenv("FPB200_STEM_GEMM") != nullptr;  // A/B measurements only
-  if (!stem_as_gemm) {
-    // stem: 7x7 s2, (6 -> 64), packed input -> phase-split 80x80x64: direct tcgen05 convolution reading its A operand
-    // in place from the input patch (stem_conv.cu)
-    StemConvPlan sp;
-    if (const char* e = build_stem_conv(A.packed, n2, stem_w_, W.host_f32("enc.stem.b", 64), A.stem, &sp)) throw std::runtime_error(e);
-    p.flops += sp.flops;
-    p.steps.push_back([sp](cudaStream_t s) { FPB_CUDA(launch_stem_conv(sp, s)); });
-    p.gemm_flops.resize(p.steps.size(), 0.0);
-    p.gemm_flops.back() = sp.flops;  // timed with the tcgen05 GEMM family (fpb200_set_gemm_profile)
-  } else {  // the same layer through the general implicit-GEMM kernel: one 64-wide K slab per filter row
-    ConvGemmDesc d;
-    d.in = A.packed;
-    d.n_img = n2; d.planes = 2; d.in_h = 80; d.in_w = 80; d.cin = 64;
-    const long long pitch_b = (long long)kStemPitch * kPackC * 2;
-    d.stride_w = 32; d.stride_plane = pitch_b; d.stride_h = 2 * pitch_b; d.stride_img = kCrop * pitch_b;
-    d.out_h = 80; d.out_w = 80; d.bw = 16; d.bh = 8; d.bn = 1;
-    taps_stem7_rows(&d);
-    d.weight = W.f16("enc.stem.w", 64, 448); d.cout = 64; d.bias = W.f32("enc.stem.b", 64);
-    d.out = A.stem; d.relu = true; d.out_phase_split = true;
-    add_gemm(p.steps, &p.flops, d);
-    // count the stem at its algorithmic size (7*7*6 MACs per output), not the padded K of 448
-    p.flops -= 2.0 * n2 * 80 * 80 * 64 * (448 - 294);
-    p.gemm_flops.back() -= 2.0 * n2 * 80 * 80 * 64 * (448 - 294);
-  }
   auto conv = [&](const __half* in, int imgs, int hw, int cin, bool s2, const std::string& name, int cout,
                   __half* out, const __half* res, int res_ld, bool phase_out, int out_ld, int img_mod, int half_coff,
                   const float* post) {
@@ -201,22 +188,90 @@ void Network::add_backbone(Plan& p, int n) {
     d.half_coff = half_coff;
     add_gemm(p.steps, &p.flops, d);
   };
-  conv(A.stem, n2, 80, 64, true, "enc.a1", 128, A.a0, nullptr, 0, false, 0, 0, 0, nullptr);
-  conv(A.a0, n2, 40, 128, false, "enc.a.r0.c1", 128, A.a1, nullptr, 0, false, 0, 0, 0, nullptr);
-  conv(A.a1, n2, 40, 128, false, "enc.a.r0.c2", 128, A.a2, A.a0, 128, false, 0, 0, 0, nullptr);
-  conv(A.a2, n2, 40, 128, false, "enc.a.r1.c1", 128, A.a1, nullptr, 0, false, 0, 0, 0, nullptr);
-  // last encodeA layer writes a || b side by side: image i < n -> channels [0,128), i >= n -> [128,256)
-  conv(A.a1, n2, 40, 128, false, "enc.a.r1.c2", 128, A.c0, A.a2, 128, false, 256, n, 128, nullptr);
-  conv(A.c0, n, 40, 256, false, "enc.ab.r0.c1", 256, A.c1, nullptr, 0, false, 0, 0, 0, nullptr);
-  conv(A.c1, n, 40, 256, false, "enc.ab.r0.c2", 256, A.c2, A.c0, 256, false, 0, 0, 0, nullptr);
-  conv(A.c2, n, 40, 256, false, "enc.ab.r1.c1", 256, A.c1, nullptr, 0, false, 0, 0, 0, nullptr);
-  conv(A.c1, n, 40, 256, false, "enc.ab.r1.c2", 256, A.c0, A.c2, 256, true, 0, 0, 0, nullptr);
-  conv(A.c0, n, 40, 256, true, "enc.ab.down", 512, A.d0, nullptr, 0, false, 0, 0, 0, nullptr);
-  conv(A.d0, n, 20, 512, false, "enc.ab.r2.c1", 512, A.d1, nullptr, 0, false, 0, 0, 0, nullptr);
-  conv(A.d1, n, 20, 512, false, "enc.ab.r2.c2", 512, A.d2, A.d0, 512, false, 0, 0, 0, nullptr);
-  conv(A.d2, n, 20, 512, false, "enc.ab.r3.c1", 512, A.d1, nullptr, 0, false, 0, 0, 0, nullptr);
-  // tokens (+ positional table) land in d0: [n, 400, 512]
-  conv(A.d1, n, 20, 512, false, "enc.ab.r3.c2", 512, A.d0, A.d2, 512, false, 0, 0, 0, W.f32("pos.table", 400, 512));
+  // ---- the layer list comes from the weight file (arch_): buffers are handed out from a pool of four, the layout
+  // each layer writes follows from its consumer (phase-split in front of a stride-2 convolution, the two branches
+  // side by side after the last encodeA layer, tokens + positional table at the very end)
+  struct Cur { const __half* buf; int imgs, hw, c; } cur{A.packed, n2, kCrop, 8};
+  int pool_next = 0;
+  auto take = [&](const __half* live0, const __half* live1) -> __half* {
+    for (int k = 0; k < 4; ++k) {
+      __half* cand = A.act[(pool_next + k) & 3];
+      if (cand != live0 && cand != live1) {
+        pool_next = (pool_next + k + 1) & 3;
+        return cand;
+      }
+    }
+    throw std::logic_error("backbone: activation pool exhausted");
+  };
+  auto first_stride_after = [&](size_t li) { return li + 1 < arch_.size() && arch_[li + 1].kind != 2 ? arch_[li + 1].stride : 1; };
+  auto fits = [&](int imgs, int hw, int c) {
+    if ((size_t)imgs * hw * hw * c * 2 > A.act_bytes) throw std::runtime_error("arch: an activation exceeds the arena buffers");
+  };
+  static const bool stem_as_gemm = getenv("FPB200_STEM_GEMM") != nullptr;  // A/B measurements only
+  size_t n_a = 0;  // layers of encodeA (tensor names count from 0 inside each section, like nn.Sequential)
+  while (n_a < arch_.size() && arch_[n_a].sec == 0) ++n_a;
+  for (size_t li = 0; li < arch_.size(); ++li) {
+    const ArchLayer& L = arch_[li];
+    const bool last = li + 1 == arch_.size();
+    const bool last_a = L.sec == 0 && (last || arch_[li + 1].sec == 1);
+    const bool phase = !last && first_stride_after(li) == 2;
+    const std::string name = std::string("enc.") + (L.sec == 0 ? "A." : "AB.") + std::to_string(L.sec == 0 ? li : li - n_a);
+    if (L.cout % 64) throw std::runtime_error("arch: channel counts must be multiples of 64");
+    if (li > 0 && arch_[li].sec < arch_[li - 1].sec) throw std::runtime_error("arch: encodeA layers must precede encodeAB");
+    const int out_ld = last_a ? 2 * L.cout : 0, img_mod = last_a ? n : 0, half_coff = last_a ? L.cout : 0;
+    const float* post = last ? W.f32("pos.table", 400, 512) : nullptr;
+    if (L.kind == 0) {
+      if (li != 0) throw std::runtime_error("arch: the 7x7 stem can only be the first layer");
+      if (last_a || last) throw std::runtime_error("arch: the stem cannot be the last layer of a section");
+      __half* out = take(nullptr, nullptr);
+      fits(n2, 80, 64);
+      if (!stem_as_gemm && phase) {
+        // 7x7 s2, (6 -> 64), packed input -> phase-split 80x80x64: direct tcgen05 convolution reading its A operand in
+        // place from the input patch (stem_conv.cu)
+        StemConvPlan sp;
+        if (const char* e = build_stem_conv(A.packed, n2, stem_w_, W.host_f32(name + ".b", 64), out, &sp)) throw std::runtime_error(e);
+        p.flops += sp.flops;
+        p.steps.push_back([sp](cudaStream_t s) { FPB_CUDA(launch_stem_conv(sp, s)); });
+        p.gemm_flops.resize(p.steps.size(), 0.0);
+        p.gemm_flops.back() = sp.flops;  // timed with the tcgen05 GEMM family (fpb200_set_gemm_profile)
+      } else {  // the same layer through the general implicit-GEMM kernel: one 64-wide K slab per filter row
+        ConvGemmDesc d;
+        d.in = A.packed;
+        d.n_img = n2; d.planes = 2; d.in_h = 80; d.in_w = 80; d.cin = 64;
+        const long long pitch_b = (long long)kStemPitch * kPackC * 2;
+        d.stride_w = 32; d.stride_plane = pitch_b; d.stride_h = 2 * pitch_b; d.stride_img = kCrop * pitch_b;
+        d.out_h = 80; d.out_w = 80; d.bw = 16; d.bh = 8; d.bn = 1;
+        taps_stem7_rows(&d);
+        d.weight = W.f16(name + ".w", 64, 448); d.cout = 64; d.bias = W.f32(name + ".b", 64);
+        d.out = out; d.relu = true; d.out_phase_split = phase;
+        add_gemm(p.steps, &p.flops, d);
+        // count the stem at its algorithmic size (7*7*6 MACs per output), not the padded K of 448
+        p.flops -= 2.0 * n2 * 80 * 80 * 64 * (448 - 294);
+        p.gemm_flops.back() -= 2.0 * n2 * 80 * 80 * 64 * (448 - 294);
+      }
+      cur = Cur{out, n2, 80, 64};
+    } else if (L.kind == 1) {
+      if (L.stride != 1 && L.stride != 2) throw std::runtime_error("arch: stride must be 1 or 2");
+      if (cur.buf == A.packed) throw std::runtime_error("arch: the first layer must be the stem");
+      const int ho = L.stride == 2 ? cur.hw / 2 : cur.hw;
+      if (ho % 4) throw std::runtime_error("arch: feature maps must stay multiples of 4 pixels");
+      __half* out = last ? A.d0 : take(cur.buf, nullptr);
+      if (!last) fits(cur.imgs, ho, L.cout);
+      conv(cur.buf, cur.imgs, cur.hw, cur.c, L.stride == 2, name, L.cout, out, nullptr, 0, phase, out_ld, img_mod, half_coff, post);
+      cur = Cur{out, last_a ? n : cur.imgs, ho, last_a ? 2 * L.cout : L.cout};
+    } else if (L.kind == 2) {
+      if (L.cout != cur.c) throw std::runtime_error("arch: a residual block keeps its channel count");
+      __half* t1 = take(cur.buf, nullptr);
+      conv(cur.buf, cur.imgs, cur.hw, cur.c, false, name + ".c1", L.cout, t1, nullptr, 0, false, 0, 0, 0, nullptr);
+      __half* out = last ? A.d0 : take(cur.buf, t1);
+      conv(t1, cur.imgs, cur.hw, cur.c, false, name + ".c2", L.cout, out, cur.buf, cur.c, phase, out_ld, img_mod, half_coff, post);
+      cur = Cur{out, last_a ? n : cur.imgs, cur.hw, last_a ? 2 * L.cout : L.cout};
+    } else {
+      throw std::runtime_error("arch: unknown layer kind");
+    }
+  }
+  if (cur.imgs != n || cur.hw != 20 || cur.c != 512)
+    throw std::runtime_error("arch: the backbone must end in 20 x 20 x 512 tokens per hypothesis (the transformer heads are fixed)");
 }
 
 namespace {

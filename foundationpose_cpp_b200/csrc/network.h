@@ -37,6 +37,14 @@ class WeightFile {
     return reinterpret_cast<const __half*>(host_.data() + (static_cast<const uint8_t*>(get(name, 0, d0, d1).dev) -
                                                             static_cast<const uint8_t*>(blob_)));
   }
+  // tensor by name without a shape expectation (nullptr when absent); host_ptr: its bytes in the host copy
+  const WeightTensor* find(const std::string& name) const {
+    auto it = tensors_.find(name);
+    return it == tensors_.end() ? nullptr : &it->second;
+  }
+  const void* host_ptr(const WeightTensor& t) const {
+    return host_.data() + (static_cast<const uint8_t*>(t.dev) - static_cast<const uint8_t*>(blob_));
+  }
   const float* host_f32(const std::string& name, int d0, int d1 = -1) const {
     return reinterpret_cast<const float*>(host_.data() + (static_cast<const uint8_t*>(get(name, 1, d0, d1).dev) -
                                                            static_cast<const uint8_t*>(blob_)));
@@ -52,9 +60,11 @@ class WeightFile {
 // Activation storage shared by both networks (they never run concurrently).
 struct Arena {
   int cap = 0;  // hypotheses
-  __half *packed = nullptr, *stem = nullptr, *a0 = nullptr, *a1 = nullptr, *a2 = nullptr, *c0 = nullptr,
-         *c1 = nullptr, *c2 = nullptr, *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *qkv = nullptr,
+  // act[]: four backbone activation buffers handed out by the plan builder (each fits the largest activation of the
+  // supported layer lists: the stem output, 2N x 80 x 80 x 64); d0: the tokens [N, 400, 512] the backbone ends in
+  __half *packed = nullptr, *act[4] = {nullptr, nullptr, nullptr, nullptr}, *d0 = nullptr, *qkv = nullptr,
          *att = nullptr, *proj = nullptr, *x1 = nullptr, *ff1 = nullptr, *ff2 = nullptr, *x2 = nullptr;
+  size_t act_bytes = 0;
   float *mean_t = nullptr, *mean_r = nullptr;
   float* mean_part = nullptr;  // partial sums of the sliced LayerNorm + token mean (few hypotheses)
   void* blob = nullptr;
@@ -66,6 +76,13 @@ struct Arena {
 enum class NetKind { kRefiner = 0, kScorer = 1 };
 
 struct Step;  // one launch of the forward sequence
+
+// One backbone layer of the weight file's "arch" table (foundationpose_cpp_b200/weights.py): section 0 = encodeA (on
+// the 2N images), 1 = encodeAB (after the channel concat); kind 0 = 7x7 ConvBNReLU on the packed crop, 1 = 3x3
+// ConvBNReLU, 2 = ResnetBasicBlock.
+struct ArchLayer {
+  int sec, kind, cout, stride;
+};
 
 class Network {
  public:
@@ -90,6 +107,7 @@ class Network {
   void add_backbone(Plan& p, int n);
   void add_encoder_layer(Plan& p, int n, const std::string& head, float* mean_out);
   NetKind kind_;
+  std::vector<ArchLayer> arch_;
   std::unique_ptr<WeightFile> w_;
   Arena* arena_;
   std::map<int, std::unique_ptr<Plan>> plans_;

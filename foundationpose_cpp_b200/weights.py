@@ -34,27 +34,70 @@ def _fold(sd: Dict[str, torch.Tensor], conv: str, bn: str, eps: float = 1e-5):
     return w, b
 
 
-def _backbone_tensors(sd, p="backbone."):
-    t = {}
-    w, b = _fold(sd, p + "encodeA.0.conv", p + "encodeA.0.bn")
-    t["enc.stem.w"], t["enc.stem.b"] = layouts.pack_stem7(w).half(), b
-    w, b = _fold(sd, p + "encodeA.1.conv", p + "encodeA.1.bn")
-    t["enc.a1.w"], t["enc.a1.b"] = layouts.pack_conv3x3(w).half(), b
-    for r, idx in enumerate((2, 3)):
-        for c in (1, 2):
-            w, b = _fold(sd, f"{p}encodeA.{idx}.conv{c}", f"{p}encodeA.{idx}.bn{c}")
-            t[f"enc.a.r{r}.c{c}.w"], t[f"enc.a.r{r}.c{c}.b"] = layouts.pack_conv3x3(w).half(), b
-    for r, idx in enumerate((0, 1)):
-        for c in (1, 2):
-            w, b = _fold(sd, f"{p}encodeAB.{idx}.conv{c}", f"{p}encodeAB.{idx}.bn{c}")
-            t[f"enc.ab.r{r}.c{c}.w"], t[f"enc.ab.r{r}.c{c}.b"] = layouts.pack_conv3x3(w).half(), b
-    w, b = _fold(sd, p + "encodeAB.2.conv", p + "encodeAB.2.bn")
-    t["enc.ab.down.w"], t["enc.ab.down.b"] = layouts.pack_conv3x3(w).half(), b
-    for r, idx in enumerate((3, 4)):
-        for c in (1, 2):
-            w, b = _fold(sd, f"{p}encodeAB.{idx}.conv{c}", f"{p}encodeAB.{idx}.bn{c}")
-            t[f"enc.ab.r{r + 2}.c{c}.w"], t[f"enc.ab.r{r + 2}.c{c}.b"] = layouts.pack_conv3x3(w).half(), b
-    t["pos.table"] = sd[p + "pe"].float()[:400]
+# Backbone layer list = DATA (SURVEY section 7, hard part a: the architecture is recalled, not given): every weight
+# file carries it as the tensor "arch", f32 [L, 4] rows (section, kind, cout, stride); csrc/network.cu builds its launch
+# plan from that table.  section 0 = encodeA (applied to the 2N images), 1 = encodeAB (after the channel concat);
+# kind 0 = 7x7 ConvBNReLU on the packed crop (first layer), 1 = 3x3 ConvBNReLU, 2 = ResnetBasicBlock.
+SEC_A, SEC_AB = 0, 1
+KIND_STEM7, KIND_CBR3, KIND_RES = 0, 1, 2
+DEFAULT_ARCH = ((SEC_A, KIND_STEM7, 64, 2), (SEC_A, KIND_CBR3, 128, 2), (SEC_A, KIND_RES, 128, 1), (SEC_A, KIND_RES, 128, 1),
+                (SEC_AB, KIND_RES, 256, 1), (SEC_AB, KIND_RES, 256, 1), (SEC_AB, KIND_CBR3, 512, 2),
+                (SEC_AB, KIND_RES, 512, 1), (SEC_AB, KIND_RES, 512, 1))
+
+
+def arch_modules(arch=DEFAULT_ARCH):
+    """[(module prefix in the state_dict, file prefix, kind, cout, stride)] - `encodeA.{i}` / `encodeAB.{i}` with i the
+    index inside the section, as nn.Sequential numbers them upstream."""
+    out, idx = [], {SEC_A: 0, SEC_AB: 0}
+    for sec, kind, cout, stride in arch:
+        sec, kind = int(sec), int(kind)
+        name = "encodeA" if sec == SEC_A else "encodeAB"
+        out.append((f"backbone.{name}.{idx[sec]}", f"enc.{'A' if sec == SEC_A else 'AB'}.{idx[sec]}", kind, int(cout), int(stride)))
+        idx[sec] += 1
+    return out
+
+
+def arch_from_state_dict(sd) -> tuple:
+    """Layer list read off a (canonical) state_dict: `...N.conv.weight` = ConvBNReLU (7x7: the stem; stride 2, as every
+    ConvBNReLU of the upstream networks has), `...N.conv1.weight` = ResnetBasicBlock."""
+    arch = []
+    for sec, name in ((SEC_A, "encodeA"), (SEC_AB, "encodeAB")):
+        i = 0
+        while True:
+            p = f"backbone.{name}.{i}"
+            if p + ".conv.weight" in sd:
+                w = sd[p + ".conv.weight"]
+                arch.append((sec, KIND_STEM7 if w.shape[2] == 7 else KIND_CBR3, int(w.shape[0]), 2))
+            elif p + ".conv1.weight" in sd:
+                arch.append((sec, KIND_RES, int(sd[p + ".conv1.weight"].shape[0]), 1))
+            else:
+                break
+            i += 1
+    if not arch:
+        raise KeyError("no backbone.encodeA / encodeAB layers in the state_dict")
+    return tuple(arch)
+
+
+def conv_order(arch=DEFAULT_ARCH):
+    """Convolution module names in forward order (ONNX files with anonymous Conv constants are matched by position)."""
+    out = []
+    for mod, _, kind, _, _ in arch_modules(arch):
+        out += [mod + ".conv"] if kind != KIND_RES else [mod + ".conv1", mod + ".conv2"]
+    return out
+
+
+def _backbone_tensors(sd, arch=None):
+    arch = arch_from_state_dict(sd) if arch is None else arch
+    t = {"arch": torch.tensor([list(map(float, r)) for r in arch], dtype=torch.float32)}
+    for mod, f, kind, cout, stride in arch_modules(arch):
+        if kind == KIND_RES:
+            for c in (1, 2):
+                w, b = _fold(sd, f"{mod}.conv{c}", f"{mod}.bn{c}")
+                t[f"{f}.c{c}.w"], t[f"{f}.c{c}.b"] = layouts.pack_conv3x3(w).half(), b
+        else:
+            w, b = _fold(sd, mod + ".conv", mod + ".bn")
+            t[f"{f}.w"], t[f"{f}.b"] = (layouts.pack_stem7(w) if kind == KIND_STEM7 else layouts.pack_conv3x3(w)).half(), b
+    t["pos.table"] = sd["backbone.pe"].float()[:400]
     return t
 
 
@@ -145,7 +188,7 @@ def positional_table(max_len: int = 400, d: int = 512) -> torch.Tensor:
     return pe
 
 
-def seeded_state_dict(kind: int, seed: int) -> Dict[str, torch.Tensor]:
+def seeded_state_dict(kind: int, seed: int, arch=DEFAULT_ARCH) -> Dict[str, torch.Tensor]:
     """Random-init state_dict with the upstream parameter names and shapes (no checkpoint is
     reachable offline): He-normal convolutions, non-trivial BatchNorm statistics, small transformer
     projections.  Used by bench.py; the tests export the oracle modules' own state_dict instead."""
@@ -182,15 +225,16 @@ def seeded_state_dict(kind: int, seed: int) -> Dict[str, torch.Tensor]:
         linear(name + ".out_proj", 512, 512)
 
     b = "backbone."
-    cbr(b + "encodeA.0", 64, 6, 7)
-    cbr(b + "encodeA.1", 128, 64, 3)
-    res(b + "encodeA.2", 128)
-    res(b + "encodeA.3", 128)
-    res(b + "encodeAB.0", 256)
-    res(b + "encodeAB.1", 256)
-    cbr(b + "encodeAB.2", 512, 256, 3)
-    res(b + "encodeAB.3", 512)
-    res(b + "encodeAB.4", 512)
+    cin = {SEC_A: 6, SEC_AB: None}
+    for mod, _, k, cout, _ in arch_modules(arch):
+        sec = SEC_A if ".encodeA." in mod else SEC_AB
+        if cin[sec] is None:
+            cin[sec] = 2 * cin[SEC_A]  # channel concat of the two branches
+        if k == KIND_RES:
+            res(mod, cout)
+        else:
+            cbr(mod, cout, cin[sec], 7 if k == KIND_STEM7 else 3)
+        cin[sec] = cout
     sd[b + "pe"] = positional_table()
     if kind == KIND_REFINER:
         for h in ("trans_head", "rot_head"):
@@ -221,11 +265,7 @@ def write_seeded(dirpath: str, refiner_seed: int = 2, scorer_seed: int = 3):
 # ----------------------------------------------------------------------------- importers
 # conv layers in forward order; ONNX exporters that fold BatchNorm leave the convolutions with
 # anonymous initializer names ("onnx::Conv_123"), so they are matched by position
-_CONV_ORDER = (["backbone.encodeA.0.conv", "backbone.encodeA.1.conv"] +
-               [f"backbone.encodeA.{i}.conv{c}" for i in (2, 3) for c in (1, 2)] +
-               [f"backbone.encodeAB.{i}.conv{c}" for i in (0, 1) for c in (1, 2)] +
-               ["backbone.encodeAB.2.conv"] +
-               [f"backbone.encodeAB.{i}.conv{c}" for i in (3, 4) for c in (1, 2)])
+_CONV_ORDER = conv_order(DEFAULT_ARCH)
 
 
 def canonical_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

@@ -8,7 +8,9 @@ f32 NHWC [N,160,160,6], outputs trans [N,3], rot [N,3] (refiner) and scores [N,1
 The layer structure below is the published NVlabs/FoundationPose architecture
 (learning/models/refine_network.py, score_network.py, network_modules.py) as recalled in SURVEY.md
 §2.3 — "parity unpinned": no ONNX / checkpoint is available in this environment to confirm it,
-so the product reads the layer list and all weights from a weight file (foundationpose_cpp_b200/weights.py).
+so the backbone's layer list is DATA on both sides: `Backbone(arch)` here, the "arch" tensor of the weight file
+(foundationpose_cpp_b200/weights.py: DEFAULT_ARCH, arch_from_state_dict) from which csrc/network.cu builds its plan.
+The transformer heads (400 tokens x 512, 4 heads) are fixed in the kernels.
 """
 from __future__ import annotations
 
@@ -52,15 +54,30 @@ def positional_table(max_len=400, d=512):
     return pe
 
 
+# (section, kind, cout, stride): section 0 = encodeA, 1 = encodeAB; kind 0 = 7x7 ConvBNReLU, 1 = 3x3 ConvBNReLU,
+# 2 = ResnetBasicBlock.  The same table as foundationpose_cpp_b200.weights.DEFAULT_ARCH (kept separate: the oracle does
+# not import the product).
+DEFAULT_ARCH = ((0, 0, 64, 2), (0, 1, 128, 2), (0, 2, 128, 1), (0, 2, 128, 1),
+                (1, 2, 256, 1), (1, 2, 256, 1), (1, 1, 512, 2), (1, 2, 512, 1), (1, 2, 512, 1))
+
+
 class Backbone(nn.Module):
     """encodeA on cat([A,B]) then encodeAB on the channel concat; returns tokens [N,400,512] + PE."""
 
-    def __init__(self):
+    def __init__(self, arch=DEFAULT_ARCH):
         super().__init__()
-        self.encodeA = nn.Sequential(ConvBNReLU(6, 64, 7, 2), ConvBNReLU(64, 128, 3, 2), ResnetBasicBlock(128),
-                                     ResnetBasicBlock(128))
-        self.encodeAB = nn.Sequential(ResnetBasicBlock(256), ResnetBasicBlock(256), ConvBNReLU(256, 512, 3, 2),
-                                      ResnetBasicBlock(512), ResnetBasicBlock(512))
+        secs, cin = {0: [], 1: []}, {0: 6, 1: None}
+        for sec, kind, cout, stride in arch:
+            if cin[sec] is None:
+                cin[sec] = 2 * cin[0]
+            if kind == 2:
+                assert cout == cin[sec], "a ResnetBasicBlock keeps its channel count"
+                secs[sec].append(ResnetBasicBlock(cout))
+            else:
+                secs[sec].append(ConvBNReLU(cin[sec], cout, 7 if kind == 0 else 3, stride))
+            cin[sec] = cout
+        self.encodeA = nn.Sequential(*secs[0])
+        self.encodeAB = nn.Sequential(*secs[1])
         self.register_buffer("pe", positional_table())
 
     def forward(self, a, b):
@@ -73,9 +90,9 @@ class Backbone(nn.Module):
 
 
 class RefineNet(nn.Module):
-    def __init__(self):
+    def __init__(self, arch=DEFAULT_ARCH):
         super().__init__()
-        self.backbone = Backbone()
+        self.backbone = Backbone(arch)
         self.trans_head = nn.Sequential(nn.TransformerEncoderLayer(512, 4, 512, dropout=0.0, batch_first=True),
                                         nn.Linear(512, 3))
         self.rot_head = nn.Sequential(nn.TransformerEncoderLayer(512, 4, 512, dropout=0.0, batch_first=True),
@@ -88,9 +105,9 @@ class RefineNet(nn.Module):
 
 
 class ScoreNet(nn.Module):
-    def __init__(self):
+    def __init__(self, arch=DEFAULT_ARCH):
         super().__init__()
-        self.backbone = Backbone()
+        self.backbone = Backbone(arch)
         self.att = nn.MultiheadAttention(512, 4, batch_first=True, bias=True)
         self.att_cross = nn.MultiheadAttention(512, 4, batch_first=True, bias=True)
         self.linear = nn.Linear(512, 1)

@@ -48,8 +48,8 @@ def test_weight_file_roundtrip_and_bn_fold():
         p = os.path.join(d, "r.fpb2w")
         weights.export_refiner(p, sd)
         t = weights.read_weight_file(p)
-    assert t["enc.stem.w"].shape == (64, 448) and t["enc.stem.w"].dtype == np.float16
-    assert t["enc.ab.r3.c2.w"].shape == (512, 4608)
+    assert t["enc.A.0.w"].shape == (64, 448) and t["enc.A.0.w"].dtype == np.float16
+    assert t["enc.AB.4.c2.w"].shape == (512, 4608)
     assert t["trans.qkv.w"].shape == (1536, 512) and t["rot.head.w"].shape == (3, 512)
     assert t["pos.table"].shape == (400, 512)
     # folded conv == conv + BN(eval) on random input
@@ -58,8 +58,8 @@ def test_weight_file_roundtrip_and_bn_fold():
     y = F.conv2d(x, w, b, stride=2, padding=1)
     y = F.batch_norm(y, sd["backbone.encodeA.1.bn.running_mean"], sd["backbone.encodeA.1.bn.running_var"],
                      sd["backbone.encodeA.1.bn.weight"], sd["backbone.encodeA.1.bn.bias"], False, 0.0, 1e-5)
-    wf = torch.from_numpy(t["enc.a1.w"].astype(np.float32)).reshape(128, 3, 3, 64).permute(0, 3, 1, 2)
-    y2 = F.conv2d(x, wf, torch.from_numpy(t["enc.a1.b"]), stride=2, padding=1)
+    wf = torch.from_numpy(t["enc.A.1.w"].astype(np.float32)).reshape(128, 3, 3, 64).permute(0, 3, 1, 2)
+    y2 = F.conv2d(x, wf, torch.from_numpy(t["enc.A.1.b"]), stride=2, padding=1)
     assert torch.allclose(y, y2, atol=2e-2, rtol=2e-2)  # fp16 weight rounding
 
 

@@ -433,3 +433,58 @@ def test_full_hd_frame_with_default_capacity(tmp_path):
         assert not ok
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("arch", [
+    # one residual block less in encodeA, one more in front of the down-sampling layer, one less after it
+    ((0, 0, 64, 2), (0, 1, 128, 2), (0, 2, 128, 1), (1, 2, 256, 1), (1, 2, 256, 1), (1, 2, 256, 1), (1, 1, 512, 2), (1, 2, 512, 1)),
+    # wider first stage, the channel concat straight after a ConvBNReLU, down-sampling as the first encodeAB layer
+    ((0, 0, 64, 2), (0, 1, 256, 2), (1, 1, 512, 2), (1, 2, 512, 1), (1, 2, 512, 1)),
+], ids=["shuffled_blocks", "short_wide"])
+def test_backbone_layer_list_is_data(tmp_path, arch):
+    """SURVEY section 7, hard part (a): the backbone is recalled, not given, so its layer list is DATA - the "arch"
+    table of the weight file, from which csrc/network.cu builds its launch plan (buffers, phase-split / concat output
+    layouts, tile shapes).  Two architectures that differ from the default one, exported from the same-arch PyTorch
+    modules, against those modules in fp32 (refiner and scorer, through the inference-core boundary)."""
+    import ctypes as C
+    from foundationpose_cpp_b200 import capi, weights
+    lib = capi.lib()
+    n = 3
+    torch.manual_seed(9)
+    a, b = torch.rand(n, 160, 160, 6), torch.rand(n, 160, 160, 6)
+    a[..., 3:] = a[..., 3:] * 2 - 1
+    b[..., 3:] = b[..., 3:] * 2 - 1
+    ad, bd = a.cuda(), b.cuda()
+    ins = (nets.nhwc_to_inputs(a.half().float()), nets.nhwc_to_inputs(b.half().float()))
+    refiner = nets.seeded_init(nets.RefineNet(arch), 12)
+    scorer = nets.seeded_init(nets.ScoreNet(arch), 13)
+    rp, sp = str(tmp_path / "r.fpb2w"), str(tmp_path / "s.fpb2w")
+    weights.export_refiner(rp, refiner.state_dict())
+    weights.export_scorer(sp, scorer.state_dict())
+    assert weights.read_weight_file(rp)["arch"].tolist() == [list(map(float, r)) for r in arch]
+    core = C.c_void_p()
+    capi.check(lib.fpb200_infer_create(rp.encode(), 0, 4, 0, C.byref(core)))
+    trans, rot = torch.zeros(n, 3, device="cuda"), torch.zeros(n, 3, device="cuda")
+    capi.check(lib.fpb200_infer_refiner(core, C.c_void_p(ad.data_ptr()), C.c_void_p(bd.data_ptr()), n,
+                                        C.c_void_p(trans.data_ptr()), C.c_void_p(rot.data_ptr())))
+    with torch.no_grad():
+        t_ref, r_ref = refiner(*ins)
+    _net_close(trans.cpu().numpy(), t_ref.numpy(), "variant arch trans")
+    _net_close(rot.cpu().numpy(), r_ref.numpy(), "variant arch rot")
+    lib.fpb200_infer_destroy(core)
+    core = C.c_void_p()
+    capi.check(lib.fpb200_infer_create(sp.encode(), 1, 4, 0, C.byref(core)))
+    scores = torch.zeros(n, device="cuda")
+    capi.check(lib.fpb200_infer_scorer(core, C.c_void_p(ad.data_ptr()), C.c_void_p(bd.data_ptr()), n, C.c_void_p(scores.data_ptr())))
+    with torch.no_grad():
+        s_ref = scorer(*ins)
+    _net_close(scores.cpu().numpy(), s_ref.numpy(), "variant arch scores")
+    lib.fpb200_infer_destroy(core)
+    # a layer list the kernels cannot run is refused at load time with a message, not run wrongly
+    bad = dict(weights.refiner_tensors(refiner.state_dict()))
+    bad["arch"] = torch.tensor([[0.0, 0, 64, 2], [0, 1, 128, 2], [1, 1, 512, 2], [1, 1, 512, 2]])  # ends in 10 x 10 tokens
+    bp = str(tmp_path / "bad.fpb2w")
+    weights.write_weight_file(bp, weights.KIND_REFINER, bad)
+    core = C.c_void_p()
+    assert lib.fpb200_infer_create(bp.encode(), 0, 4, 0, C.byref(core)) != 0
+    assert b"arch" in lib.fpb200_last_error() or b"tensor" in lib.fpb200_last_error()
