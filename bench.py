@@ -354,6 +354,26 @@ def extra_single_gpu(args, model, mesh, rgb_p, depth_p, mask_p, gt, K, rp, sp, l
                                 "p99_ms": float(np.percentile(lat, 99) * 1e3), "launches_per_call": model.last_launch_count(),
                                 "published_reference_rtx4060_fps": 220,
                                 "protocol": "simple_tests/src/test_foundationpose.cpp:130-155 (consecutive Track calls, host buffers)"}
+        # the same frames as a stream (fpb200_track_stream_*): upload of frame k + 1 on a copy stream while frame k is
+        # refined, pose chained in device memory, two frames in flight (host buffers, results read back every frame)
+        try:
+            rgb_q, depth_q = _pin(rgb_p.copy()), _pin(depth_p.copy())  # two pinned host frames, alternating
+            hostf = [(rgb_p, depth_p), (rgb_q, depth_q)]
+            for rep in range(2):
+                n_s = 40 if rep == 0 else calls
+                model.track_stream_begin(pose, name, 1)
+                model.track_stream_push(*hostf[0])
+                t0 = time.perf_counter()
+                for i in range(1, n_s):
+                    model.track_stream_push(*hostf[i & 1])
+                    model.track_stream_pop()
+                model.track_stream_pop()
+                dt_s = time.perf_counter() - t0
+            out["config3_track"]["stream"] = {"value": (calls - 1) / dt_s, "unit": "fps", "frames": calls,
+                                               "what": "fpb200_track_stream_push / pop, two frames in flight: double-buffered "
+                                                       "upload on a copy stream, refined pose chained on the device"}
+        except Exception as e:  # pragma: no cover
+            out["config3_track"]["stream"] = {"unavailable": str(e)}
     except Exception as e:  # pragma: no cover
         out["config3_track"] = {"unavailable": str(e)}
     # ---- config 4 on one GPU: the 10k-triangle mesh (the N = 1 point of the sharded curve)

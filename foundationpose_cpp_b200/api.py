@@ -221,6 +221,21 @@ class FoundationPose:
         capi.check(self._lib.fpb200_track_wait(self._h, _fptr(out)))
         return out.reshape(4, 4).T.copy()
 
+    # ---- streamed tracking (fpb200_track_stream_*) ------------------------------------------
+    def track_stream_begin(self, hyp_pose_in_mesh, target_name: str, refine_itr: int = 1):
+        hyp = np.ascontiguousarray(np.asarray(hyp_pose_in_mesh, np.float32).T)
+        capi.check(self._lib.fpb200_track_stream_begin(self._h, _fptr(hyp), target_name.encode(), int(refine_itr)))
+
+    def track_stream_push(self, rgb, depth):
+        """rgb / depth: C-contiguous u8 [h,w,3] / f32 [h,w] arrays that stay alive until the matching pop."""
+        h, w = depth.shape
+        capi.check(self._lib.fpb200_track_stream_push(self._h, _fptr(rgb), _fptr(depth), h, w))
+
+    def track_stream_pop(self) -> np.ndarray:
+        out = np.zeros(16, np.float32)
+        capi.check(self._lib.fpb200_track_stream_pop(self._h, _fptr(out)))
+        return out.reshape(4, 4).T.copy()
+
     # ---- stage API (tests, multi-GPU) ----------------------------------------------------
     def upload(self, rgb, depth):
         rgb, depth, _ = self._check_images(rgb, depth)

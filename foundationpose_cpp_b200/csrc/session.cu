@@ -260,6 +260,20 @@ struct fpb200_session {
   // events; inside a capture this becomes a parallel branch of the CUDA graph)
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // streamed tracking (fpb200_track_stream_*): frames alternate between the primary buffers and a second set, uploaded
+  // on copy_stream while the previous frame is still being refined; results go through a ring of pinned slots
+  static constexpr int kStreamRing = 4;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_result[kStreamRing] = {};
+  DevBuf<uint8_t> rgb_alt;
+  DevBuf<float> depth_alt, xyz_alt;
+  uint8_t* f_rgb = nullptr;   // frame buffers the kernels of the current call read (primary or alternate set)
+  float *f_depth = nullptr, *f_xyz = nullptr;
+  float (*stream_poses)[16] = nullptr;  // pinned [kStreamRing][16]
+  long long stream_pushed = 0, stream_popped = 0;
+  bool stream_open = false;
+  int stream_itr = 1;
+  MeshEntry* stream_mesh = nullptr;
   cudaEvent_t ev[kNumStages + 1]{};
   bool ev_valid[kNumStages + 1]{};
   std::vector<std::unique_ptr<MeshEntry>> meshes;
@@ -318,6 +332,11 @@ struct fpb200_session {
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
     if (host_result) cudaFreeHost(host_result);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto e : ev_copied) if (e) cudaEventDestroy(e);
+    for (auto e : ev_consumed) if (e) cudaEventDestroy(e);
+    for (auto e : ev_result) if (e) cudaEventDestroy(e);
+    if (stream_poses) cudaFreeHost(stream_poses);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (side_stream) cudaStreamDestroy(side_stream);
@@ -378,6 +397,8 @@ void do_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h,
     projection_matrix(s->K, h, w, s->intr.proj);
   }
   s->mark(0);
+  s->f_rgb = s->rgb.p; s->f_depth = s->depth.p; s->f_xyz = s->xyz.p;  // (a streamed call may have left the alternates)
+  s->stream_open = false;  // an ordinary call ends a frame stream
   FPB_CUDA(cudaMemcpyAsync(s->rgb.p, rgb, (size_t)h * w * 3, cudaMemcpyHostToDevice, s->stream));
   FPB_CUDA(cudaMemcpyAsync(s->depth.p, depth, sizeof(float) * (size_t)h * w, cudaMemcpyHostToDevice, s->stream));
   s->uploaded = true;
@@ -385,7 +406,7 @@ void do_upload(fpb200_session* s, const uint8_t* rgb, const float* depth, int h,
 
 void do_xyz(fpb200_session* s) {
   FPB_NVTX("fpb200/depth_to_xyz");
-  launch_depth_to_xyz(s->depth.p, s->xyz.p, s->img_h, s->img_w, s->intr, s->stream);
+  launch_depth_to_xyz(s->f_depth, s->f_xyz, s->img_h, s->img_w, s->intr, s->stream);
   s->count_launches(1);
   s->mark(1);
 }
@@ -404,7 +425,7 @@ void do_sample(fpb200_session* s, MeshEntry* mesh) {
   // one filter kernel (erode + bilateral; the eroded image stays on chip), one scan, one select that also writes
   // the hypotheses
   const int n = std::min(kGridPoses, s->opt.max_hyps);
-  launch_depth_filters(s->depth.p, nullptr, s->filtered.p, h, w, reinterpret_cast<int*>(s->sampler_scratch.p), s->stream);
+  launch_depth_filters(s->f_depth, nullptr, s->filtered.p, h, w, reinterpret_cast<int*>(s->sampler_scratch.p), s->stream);
   launch_guess_translation(s->filtered.p, s->mask.p, h, w, s->intr, s->center.p, s->status.p, s->sampler_scratch.p,
                            s->grid.p, s->poses.p, n, s->stream);
   s->count_launches(3);
@@ -422,7 +443,7 @@ void do_render_and_transform(fpb200_session* s, float crop_ratio) {
   // fork: warp (HBM-bound, reads the frame) beside the rasteriser (latency-bound, reads the mesh); both only need aux
   FPB_CUDA(cudaEventRecord(s->ev_fork, s->stream));
   FPB_CUDA(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
-  launch_warp(s->rgb.p, s->xyz.p, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->side_stream);
+  launch_warp(s->f_rgb, s->f_xyz, s->img_h, s->img_w, s->aux.p, nl, m.dm.diameter, s->arena->packed, nl, s->side_stream);
   FPB_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
   const int k_render = launch_render(m.dm, s->aux.p, nl, s->vrec.p, s->arena->packed, 0,
                                      s->debug_ids ? s->rast_id.p : nullptr, s->status.p, s->zbuf.p, kSplitRenderPoses,
@@ -720,6 +741,7 @@ int fpb200_create(const fpb200_mesh* meshes, int num_meshes, const float K[9], i
     const size_t px = (size_t)max_h * max_w;
     const int cap = s->opt.max_hyps;
     s->rgb.alloc(px * 3); s->mask.alloc(px); s->depth.alloc(px); s->xyz.alloc(px * 3);
+    s->f_rgb = s->rgb.p; s->f_depth = s->depth.p; s->f_xyz = s->xyz.p;
     s->filtered.alloc(px); s->sampler_scratch.alloc(px + 8);
     const std::vector<float> grid = make_rotation_grid();
     s->grid.upload(grid.data(), grid.size());
@@ -891,6 +913,93 @@ int fpb200_track_wait(fpb200_session* s, float out_pose[16]) {
   });
 }
 
+// ---- streamed tracking: SURVEY section 8 f4 (double-buffered upload, frame k + 1 in flight while frame k is refined)
+int fpb200_track_stream_begin(fpb200_session* s, const float hyp_pose[16], const char* target_name, int refine_itr) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && hyp_pose, "null session / pose");
+    MeshEntry* mesh = s->find_mesh(target_name);
+    FPB_REQUIRE(mesh, "unknown target '%s'", target_name ? target_name : "(null)");
+    FPB_REQUIRE(refine_itr >= 1, "refine_itr must be >= 1");
+    FPB_CUDA(cudaStreamSynchronize(s->stream));
+    if (!s->copy_stream) {
+      const size_t px = (size_t)s->max_h * s->max_w;
+      FPB_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+      for (auto& e : s->ev_copied) FPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& e : s->ev_consumed) FPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& e : s->ev_result) FPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      FPB_CUDA(cudaMallocHost(&s->stream_poses, sizeof(float) * 16 * fpb200_session::kStreamRing));
+      s->rgb_alt.alloc(px * 3);
+      s->depth_alt.alloc(px);
+      s->xyz_alt.alloc(px * 3);
+    }
+    memcpy(s->host_result->hyp, hyp_pose, sizeof(float) * 16);
+    FPB_CUDA(cudaMemcpyAsync(s->poses.p, s->host_result->hyp, sizeof(float) * 16, cudaMemcpyHostToDevice, s->stream));
+    // both frame buffer sets are free
+    for (auto& e : s->ev_consumed) FPB_CUDA(cudaEventRecord(e, s->stream));
+    s->stream_mesh = mesh;
+    s->stream_itr = refine_itr;
+    s->stream_pushed = s->stream_popped = 0;
+    s->stream_open = true;
+    s->pending_async = false;
+    return FPB200_OK;
+  });
+}
+
+int fpb200_track_stream_push(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && rgb && depth, "null argument");
+    if (!s->stream_open) return fail(FPB200_ERR_STATE, "fpb200_track_stream_begin must be called first");
+    if (s->stream_pushed - s->stream_popped >= 2)
+      return fail(FPB200_ERR_STATE, "two frames are in flight: call fpb200_track_stream_pop first");
+    FPB_REQUIRE(h > 0 && w > 0 && h <= s->max_h && w <= s->max_w, "image %dx%d exceeds the session capacity %dx%d", h, w,
+                s->max_h, s->max_w);
+    if (h != s->img_h || w != s->img_w) {
+      FPB_REQUIRE(s->stream_pushed == s->stream_popped, "the image size may only change while no frame is in flight");
+      s->img_h = h; s->img_w = w; s->intr.img_h = h; s->intr.img_w = w;
+      projection_matrix(s->K, h, w, s->intr.proj);
+    }
+    const int par = (int)(s->stream_pushed & 1);
+    uint8_t* d_rgb = par ? s->rgb_alt.p : s->rgb.p;
+    float* d_depth = par ? s->depth_alt.p : s->depth.p;
+    // upload on the copy stream as soon as the frame that last used this buffer set has been consumed
+    FPB_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_consumed[par], 0));
+    FPB_CUDA(cudaMemcpyAsync(d_rgb, rgb, (size_t)h * w * 3, cudaMemcpyHostToDevice, s->copy_stream));
+    FPB_CUDA(cudaMemcpyAsync(d_depth, depth, sizeof(float) * (size_t)h * w, cudaMemcpyHostToDevice, s->copy_stream));
+    FPB_CUDA(cudaEventRecord(s->ev_copied[par], s->copy_stream));
+    // refine on the session stream; the hypothesis is the pose the previous frame left in device memory
+    FPB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_copied[par], 0));
+    s->launches = 0;
+    s->f_rgb = d_rgb; s->f_depth = d_depth; s->f_xyz = par ? s->xyz_alt.p : s->xyz.p;
+    s->uploaded = true;
+    s->cur_mesh = s->stream_mesh;
+    s->n_hyp = 1; s->lo = 0; s->hi = 1; s->shard_cap = 1; s->features_ready = false;
+    const int slot = (int)(s->stream_pushed % fpb200_session::kStreamRing);
+    char key[160];
+    snprintf(key, sizeof(key), "track_stream:%d:%dx%d:%p:%d:%d", s->stream_itr, h, w, (void*)s->stream_mesh, par, slot);
+    run_maybe_graphed(s, key, [&]() {
+      do_xyz(s);
+      for (int i = 0; i < s->stream_itr; ++i) do_refine_step(s);
+      FPB_CUDA(cudaMemcpyAsync(s->stream_poses[slot], s->poses.p, sizeof(float) * 16, cudaMemcpyDeviceToHost, s->stream));
+    });
+    FPB_CUDA(cudaEventRecord(s->ev_consumed[par], s->stream));
+    FPB_CUDA(cudaEventRecord(s->ev_result[slot], s->stream));
+    ++s->stream_pushed;
+    return FPB200_OK;
+  });
+}
+
+int fpb200_track_stream_pop(fpb200_session* s, float out_pose[16]) {
+  return guard([&]() -> int {
+    FPB_REQUIRE(s && out_pose, "null session / output");
+    if (!s->stream_open || s->stream_popped >= s->stream_pushed) return fail(FPB200_ERR_STATE, "no frame is in flight");
+    const int slot = (int)(s->stream_popped % fpb200_session::kStreamRing);
+    FPB_CUDA(cudaEventSynchronize(s->ev_result[slot]));
+    memcpy(out_pose, s->stream_poses[slot], sizeof(float) * 16);
+    ++s->stream_popped;
+    return FPB200_OK;
+  });
+}
+
 int fpb200_track(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w, const float hyp_pose[16],
                  const char* target_name, int refine_itr, float out_pose[16]) {
   if (!out_pose) return fail(FPB200_ERR_INVALID, "null output");
@@ -1013,7 +1122,7 @@ int fpb200_read_buffer(fpb200_session* s, const char* name, void* host_dst, size
     const size_t img_b = (size_t)kPackImageElems * 2;
     if (nm == "render_input") { src = s->arena->packed; bytes = img_b * nl; }
     else if (nm == "transf_input") { src = s->arena->packed + (size_t)nl * kPackImageElems; bytes = img_b * nl; }
-    else if (nm == "xyz_map") { src = s->xyz.p; bytes = sizeof(float) * 3 * s->img_h * s->img_w; }
+    else if (nm == "xyz_map") { src = s->f_xyz; bytes = sizeof(float) * 3 * s->img_h * s->img_w; }
     else if (nm == "depth_filtered") { src = s->filtered.p; bytes = sizeof(float) * s->img_h * s->img_w; }
     else if (nm == "scores") { src = s->scores.p; bytes = sizeof(float) * s->n_hyp; }
     else if (nm == "trans") { src = s->trans.p; bytes = sizeof(float) * 3 * nl; }

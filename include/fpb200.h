@@ -96,6 +96,16 @@ int fpb200_track_async(fpb200_session* s, const uint8_t* rgb, const float* depth
                        const float hyp_pose[16], const char* target_name, int refine_itr);
 int fpb200_track_wait(fpb200_session* s, float out_pose[16]);
 
+/* Tracking as a STREAM of frames (the reference would use EasyDeploy's async pipeline,
+ * deploy_core/async_pipeline.h:78-242, around fp/src/foundationpose.cpp:230-265): frame k + 1 is uploaded on a copy
+ * stream into a second set of frame buffers while frame k is still being refined, the refined pose stays in device memory
+ * as the hypothesis of the next frame (no host round trip), results are delivered in order.  At most two frames are in
+ * flight; rgb / depth of a pushed frame must stay valid until its pop returns (pinned memory makes the upload truly
+ * asynchronous).  The poses equal those of consecutive fpb200_track calls that feed each result back in. */
+int fpb200_track_stream_begin(fpb200_session* s, const float hyp_pose[16], const char* target_name, int refine_itr);
+int fpb200_track_stream_push(fpb200_session* s, const uint8_t* rgb, const float* depth, int h, int w);
+int fpb200_track_stream_pop(fpb200_session* s, float out_pose[16]);
+
 /* ---- stage-level entry points (the reference's private seams), used by tests / multi-GPU ---- */
 
 /* UploadDataToDevice + depth->xyz (fp/src/foundationpose.cpp:267-315, fp/src/foundationpose_utils.cu:3-75). */

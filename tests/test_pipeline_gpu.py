@@ -488,3 +488,43 @@ def test_backbone_layer_list_is_data(tmp_path, arch):
     core = C.c_void_p()
     assert lib.fpb200_infer_create(bp.encode(), 0, 4, 0, C.byref(core)) != 0
     assert b"arch" in lib.fpb200_last_error() or b"tensor" in lib.fpb200_last_error()
+
+
+def test_track_stream_equals_consecutive_track_calls(env):
+    """fpb200_track_stream_* - frame k + 1 uploaded on a copy stream into the second buffer set
+    while frame k is refined, the refined pose chained in device memory.  10 frames (noisy copies of the scene, so that
+    consecutive uploads differ), two in flight: every pose must equal, bit for bit, consecutive Track calls that feed
+    each result back in through the host; eager, captured and replayed calls of all four graph variants are covered.
+    Then an ordinary Track on the same session, and the error paths."""
+    m = env["model"]
+    rng = np.random.default_rng(5)
+    frames = []
+    for k in range(10):
+        rgb = np.clip(env["rgb"].astype(np.int16) + rng.integers(-3, 4, env["rgb"].shape), 0, 255).astype(np.uint8)
+        depth = (env["depth"] + (env["depth"] > 0) * rng.normal(0, 2e-4, env["depth"].shape)).astype(F)
+        frames.append((np.ascontiguousarray(rgb), np.ascontiguousarray(depth)))
+    start = synth.perturb_pose(env["gt"], 3.0, 0.005, 7)
+    want, pose = [], start
+    for rgb, depth in frames:
+        ok, pose = m.Track(rgb, depth, pose, "mustard_proxy", refine_itr=2)
+        assert ok, m.last_error
+        want.append(pose)
+    assert any(not np.array_equal(want[i], want[i + 1]) for i in range(9))
+    for rep in range(2):  # the second round replays the CUDA graphs captured by the first
+        m.track_stream_begin(start, "mustard_proxy", 2)
+        got = []
+        m.track_stream_push(*frames[0])
+        for k in range(1, 10):
+            m.track_stream_push(*frames[k])  # two in flight
+            got.append(m.track_stream_pop())
+        with pytest.raises(api.capi.FpbError):
+            m.track_stream_push(*frames[0]); m.track_stream_push(*frames[1])  # a third frame in flight is refused
+        got.append(m.track_stream_pop())
+        got_extra = m.track_stream_pop()  # the frame pushed inside the raises block above
+        assert np.isfinite(got_extra).all()
+        with pytest.raises(api.capi.FpbError):
+            m.track_stream_pop()
+        for k in range(10):
+            assert np.array_equal(got[k], want[k]), (rep, k)
+    ok, pose = m.Track(frames[0][0], frames[0][1], start, "mustard_proxy", refine_itr=2)
+    assert ok and np.array_equal(pose, want[0])
