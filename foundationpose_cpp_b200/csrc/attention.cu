@@ -545,7 +545,16 @@ const char* make_params(const __half* qkv, __half* out, int n_hyp, int qkv_ld, i
 
 }  // namespace tc
 
-const char* attention_init() { return tc::init(); }
+namespace tc2 {
+const char* init();
+const char* make_params(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, AttentionPlan* p);
+void launch(const AttentionPlan& plan, cudaStream_t s);
+}  // namespace tc2
+
+const char* attention_init() {
+  if (const char* e = tc::init()) return e;
+  return tc2::init();
+}
 
 namespace {
 unsigned long long* g_phase_clocks = nullptr;  // device buffer, only with FPB200_ATTN_PHASES=1
@@ -562,17 +571,31 @@ bool attention_phase_clocks(unsigned long long out[22]) {
 
 const char* build_attention(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, AttentionPlan* plan) {
   if (n_hyp <= 0) return "attention: no hypotheses";
-  if (const char* e = tc::init()) return e;
-  return tc::make_params(qkv, out, n_hyp, qkv_ld, out_ld, plan);
+  if (const char* e = attention_init()) return e;
+  if (const char* e = tc::make_params(qkv, out, n_hyp, qkv_ld, out_ld, plan)) return e;
+  if (const char* e = tc2::make_params(qkv, out, n_hyp, qkv_ld, out_ld, plan)) return e;
+  // FPB200_ATTN_V2=1 selects the second design (attention2.cu: measured slower so far, kept with its tests - see
+  // DESIGN.md section 8); read per plan, never per launch
+  const char* v2 = getenv("FPB200_ATTN_V2");
+  plan->version = v2 && v2[0] == '1' ? 2 : 1;
+  return nullptr;
 }
 
 void launch_attention(const AttentionPlan& plan, cudaStream_t s) {
   if (plan.n_items <= 0) return;
-  tc::Params prm = plan;
   static const bool want_phases = getenv("FPB200_ATTN_PHASES") != nullptr;
+  if (plan.version == 2 && !want_phases) {
+    tc2::launch(plan, s);
+    return;
+  }
+  tc::Params prm = plan;
   if (want_phases) {
     if (!g_phase_clocks) cudaMalloc(&g_phase_clocks, 24 * sizeof(unsigned long long));
     prm.phase_clocks = g_phase_clocks;
+  }
+  if (plan.version == 2) {
+    tc2::launch(prm, s);
+    return;
   }
   const int grid = prm.n_items < tc::g_num_sms ? prm.n_items : tc::g_num_sms;
   tc::attention_tc_kernel<<<grid, tc::kThreads, tc::kSmem, s>>>(prm);

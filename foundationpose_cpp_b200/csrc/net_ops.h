@@ -19,6 +19,17 @@ struct AttentionPlan {
   CUtensorMap tm_out;  // out as (out_ld, 400, n_hyp), box (64, 32, 1): one softmax warp's rows x one dim half
   int n_items = 0;     // n_hyp * heads * query tiles
   unsigned long long* phase_clocks = nullptr;  // optional (FPB200_ATTN_PHASES=1): per-phase clock sums of CTA 0
+  // second design (attention2.cu: K / V resident in shared memory, Q in tensor memory, S computed twice)
+  CUtensorMap tm_kv64;  // qkv, box (64, 64, 1)
+  CUtensorMap tm_kv16;  // qkv, box (64, 16, 1): keys 384..399
+  const __half* qkv = nullptr;
+  __half* out = nullptr;
+  int qkv_ld = 0, out_ld = 0;
+  int tiles_per_cta = 4;  // query tiles of one (hypothesis, head) walked by one CTA: 4, 2 or 1
+  int tpc_log2 = 2;
+  int n_units = 0;        // n_hyp * heads * (4 / tiles_per_cta)
+  int grid = 0;
+  int version = 2;        // 1: attention.cu (FPB200_ATTN_V1=1), 2: attention2.cu
 };
 const char* build_attention(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, AttentionPlan* plan);
 void launch_attention(const AttentionPlan& plan, cudaStream_t s);

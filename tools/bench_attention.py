@@ -10,7 +10,19 @@ out = torch.empty(n, 400, 512, device="cuda", dtype=torch.float16)
 ms = capi.debug_attention(qkv.data_ptr(), out.data_ptr(), n, 20)
 fl = 2.0 * n * 4 * 2 * 400 * 400 * 128
 print(f"attention n={n}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s (algorithmic)")
-if os.environ.get("FPB200_ATTN_PHASES"):
+if os.environ.get("FPB200_ATTN_PHASES") and os.environ.get("FPB200_ATTN_V2", "0") == "1":
+    import ctypes as C
+    buf = (C.c_ulonglong * 22)()
+    capi.check(capi.lib().fpb200_debug_attention_phases(buf))
+    items = max(1, buf[7])
+    mn = ["wait K/Q", "-", "-", "wait V", "wait P", "wait O free", "issue/other"]
+    print(f"attention2, CTA 0, {items} items; SM clocks per item")
+    print("  MMA thread B: " + ", ".join(f"{nm} {buf[i] / items:.0f}" for i, nm in enumerate(mn) if nm != "-") + f"; total {sum(buf[0:7]) / items:.0f}")
+    print("  MMA thread A: " + ", ".join(f"{nm} {buf[18 + i] / items:.0f}" for i, nm in enumerate(["wait K/Q", "wait S_A free", "issue/other"])))
+    print("  set B (exp): " + ", ".join(f"{nm} {buf[8 + i] / items:.0f}" for i, nm in enumerate(["waits (max, S_B)", "tcgen05.ld + wait", "exp2 / convert / sum", "tcgen05.st + wait, fence, arrive"])))
+    an = ["wait S_A", "pass A compute / other", "wait Q free", "wait O + sum", "epilogue", "(pre-epilogue)"]
+    print("  set A: " + ", ".join(f"{nm} {buf[12 + i] / items:.0f}" for i, nm in enumerate(an)))
+elif os.environ.get("FPB200_ATTN_PHASES"):
     import ctypes as C
     buf = (C.c_ulonglong * 22)()
     capi.check(capi.lib().fpb200_debug_attention_phases(buf))
