@@ -143,6 +143,30 @@ def test_refiner_and_pose_update_parity(env):
         assert np.abs(got[i][:3, 3] - ref[i][:3, 3]).max() <= 5e-4
 
 
+def test_refiner_with_second_attention_kernel(env, tmp_path, monkeypatch):
+    """attention2.cu (FPB200_ATTN_V2=1, read when a session builds its plans) as a drop-in inside the refiner: same
+    outputs as the fp32 modules (same tolerance as the default kernel) on the same hypotheses."""
+    monkeypatch.setenv("FPB200_ATTN_V2", "1")
+    rp, sp = helpers.write_seeded_weights(str(tmp_path))
+    m = api.CreateFoundationPoseModel(rp, sp, [api.ArrayMeshLoader.from_mesh_data(env["mesh"])], env["K"], max_h=480,
+                                      max_w=640)
+    try:
+        refiner, _ = helpers.seeded_nets()
+        m.upload(env["rgb"], env["depth"])
+        poses = O.sample_hypotheses(env["depth"], env["mask"], env["K"])[:5]
+        m.set_hypotheses(poses, "mustard_proxy")
+        m.refine_step()
+        n = len(poses)
+        a = torch.from_numpy(m.read_packed("render_input", n))
+        b = torch.from_numpy(m.read_packed("transf_input", n))
+        with torch.no_grad():
+            t_ref, r_ref = refiner(nets.nhwc_to_inputs(a), nets.nhwc_to_inputs(b))
+        _net_close(m.read_buffer("trans", np.float32, n * 3).reshape(n, 3), t_ref.numpy(), "trans (attention2)")
+        _net_close(m.read_buffer("rot", np.float32, n * 3).reshape(n, 3), r_ref.numpy(), "rot (attention2)")
+    finally:
+        m.close()
+
+
 def test_scorer_parity_and_argmax(env):
     m = env["model"]
     _, scorer = helpers.seeded_nets()
