@@ -490,7 +490,6 @@ using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-int g_num_sms = 0;
 std::mutex g_mu;
 
 const char* init() {
@@ -511,7 +510,6 @@ const char* init() {
   if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) !=
       cudaSuccess)
     return "cudaFuncSetAttribute(attention smem) failed (not an sm_100a device?)";
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (dev < 64) inited |= 1ull << dev;
   return nullptr;
 }
@@ -549,6 +547,7 @@ namespace tc2 {
 const char* init();
 const char* make_params(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, AttentionPlan* p);
 void launch(const AttentionPlan& plan, cudaStream_t s);
+int device_sms();
 }  // namespace tc2
 
 const char* attention_init() {
@@ -576,6 +575,7 @@ const char* build_attention(const __half* qkv, __half* out, int n_hyp, int qkv_l
   if (const char* e = tc2::make_params(qkv, out, n_hyp, qkv_ld, out_ld, plan)) return e;
   // FPB200_ATTN_V2=1 selects the second design (attention2.cu: measured slower so far, kept with its tests - see
   // DESIGN.md section 8); read per plan, never per launch
+  plan->grid_v1 = plan->n_items < tc2::device_sms() ? plan->n_items : tc2::device_sms();  // SM count of THIS device
   const char* v2 = getenv("FPB200_ATTN_V2");
   plan->version = v2 && v2[0] == '1' ? 2 : 1;
   return nullptr;
@@ -597,8 +597,7 @@ void launch_attention(const AttentionPlan& plan, cudaStream_t s) {
     tc2::launch(prm, s);
     return;
   }
-  const int grid = prm.n_items < tc::g_num_sms ? prm.n_items : tc::g_num_sms;
-  tc::attention_tc_kernel<<<grid, tc::kThreads, tc::kSmem, s>>>(prm);
+  tc::attention_tc_kernel<<<prm.grid_v1, tc::kThreads, tc::kSmem, s>>>(prm);
 }
 
 }  // namespace fpb

@@ -614,10 +614,15 @@ const char* init() {
   return nullptr;
 }
 
-const char* make_params(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, AttentionPlan* p) {
+// SM count of the current device (after init() on it)
+int device_sms() {
   int dev = 0;
   cudaGetDevice(&dev);
-  const int sms = dev < 64 && g_sms[dev] ? g_sms[dev] : 148;
+  return dev >= 0 && dev < 64 && g_sms[dev] ? g_sms[dev] : 148;
+}
+
+const char* make_params(const __half* qkv, __half* out, int n_hyp, int qkv_ld, int out_ld, AttentionPlan* p) {
+  const int sms = device_sms();
   cuuint64_t dims[3] = {(cuuint64_t)qkv_ld, (cuuint64_t)kTok, (cuuint64_t)n_hyp};
   cuuint64_t strides[2] = {(cuuint64_t)qkv_ld * 2, (cuuint64_t)qkv_ld * 2 * kTok};
   cuuint32_t es[3] = {1, 1, 1};
