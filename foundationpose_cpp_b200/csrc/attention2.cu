@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention2_kernel(const __grid_co
       ptx::mbar_init(bar(kBarSAFree + s), 4);
       ptx::mbar_init(bar(kBarSBFull + s), 1);
       ptx::mbar_init(bar(kBarPFull + s), 8);
-      ptx::mbar_init(bar(kBarMax + s), 4);
-      ptx::mbar_init(bar(kBarSum + s), 8);
+      ptx::mbar_init(bar(kBarMax + s), 128);  // every thread that wrote a row maximum arrives itself
+      ptx::mbar_init(bar(kBarSum + s), 256);  // ... and every thread that wrote a partial row sum
     }
     ptx::mbar_init(bar(kBarOFull), 1);
     ptx::mbar_init(bar(kBarOFree), 4);
@@ -412,8 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention2_kernel(const __grid_co
         ++ga;
       }
       row_max[(it & 1) * kQT + row] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c_log2;
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(kBarMax + (it & 1)));
+      ptx::mbar_arrive(bar(kBarMax + (it & 1)));  // release by the writer itself
     };
     auto epilogue = [&](int it, const Item& im) {
       const bool active = im.qt * kQT + q * 32 < kTok;
@@ -568,8 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention2_kernel(const __grid_co
         ++gb;
       }
       row_sum[(half * 2 + (it & 1)) * kQT + row] = sum;
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(kBarSum + (it & 1)));
+      ptx::mbar_arrive(bar(kBarSum + (it & 1)));  // release by the writer itself
     }
     tick(3);
     if (timed)
