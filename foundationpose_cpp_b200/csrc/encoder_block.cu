@@ -665,8 +665,9 @@ const char* build_encoder_block(const EncoderBlockDesc& d, EncoderBlockPlan* pla
   memset(&p, 0, sizeof(p));
   const long long rows = (long long)d.n_hyp * 400;
   const int n_blocks = (int)((rows + kBM - 1) / kBM);
-  // CTA pairs (half the weight traffic per SM) once there is more than one wave of single CTAs
-  const bool pair = d.mode == 0 ? n_blocks >= 2 * g_num_sms : d.mode == 2;
+  // CTA pairs (half the weight traffic per SM): measured faster at every size (N = 1: 34.9 vs 38.6 us, 32: 39.6 vs
+  // 42.7, 63: 67.6 vs 74.5, 252: 197 vs 210), so single CTAs remain only as mode 1 for tests / A-B runs
+  const bool pair = d.mode == 0 ? n_blocks >= 2 : d.mode == 2;
   const int cs = pair ? 2 : 1;
   if (const char* e = encode_2d(&p.tm_att, d.att, kD, rows, 64, kBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
   if (const char* e = encode_2d(&p.tm_x0, d.x0, kD, rows, 64, kBM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
