@@ -180,7 +180,15 @@ void Network::add_backbone(Plan& p, int n) {
     const int ho = s2 ? hw / 2 : hw;
     d.in_h = ho; d.in_w = ho; d.planes = s2 ? 4 : 1;
     d.out_h = ho; d.out_w = ho;
-    if (ho % 8 == 0) { d.bw = 8; d.bh = 8; d.bn = 2; } else { d.bw = 4; d.bh = 4; d.bn = 8; }
+    // 128-row tiles = bw x bh pixels of bn images.  Maps that are not multiples of 8 pixels (20 x 20) take 4 x 4 pixels
+    // of 8 images - unless the launch has fewer images than that (Track, N <= 2 hypotheses): 25 tiles per image
+    // GROUP with 1/8 .. 4/8 of their rows in use cost two waves of CTAs on the 512-channel layers, so few images take
+    // partial 8 x 8 x 2 (9 tiles per image pair) or 16 x 8 x 1 (6 per image) tiles instead.  The accumulation order of
+    // an output element does not depend on the tile shape.
+    if (ho % 8 == 0) { d.bw = 8; d.bh = 8; d.bn = 2; }
+    else if (imgs == 1) { d.bw = 16; d.bh = 8; d.bn = 1; }
+    else if (imgs <= 4) { d.bw = 8; d.bh = 8; d.bn = 2; }
+    else { d.bw = 4; d.bh = 4; d.bn = 8; }
     if (s2) taps_3x3_s2_phase(&d); else taps_3x3_s1(&d);
     d.weight = W.f16(name + ".w", cout, 9 * cin); d.cout = cout; d.bias = W.f32(name + ".b", cout);
     d.residual = res; d.res_ld = res_ld; d.post_add = post;

@@ -82,6 +82,10 @@ def test_linear(rows, k, cout, relu, cluster, block_n):
     (3, 40, 256, 256, (8, 8, 2), True, False),
     (3, 20, 512, 512, (4, 4, 8), True, True),
     (2, 80, 64, 64, (16, 8, 1), False, False),
+    # the tile shapes picked for 20 x 20 maps with 1 .. 4 images (Track, N = 1 / 2): partial tiles in x and y
+    (1, 20, 512, 512, (16, 8, 1), True, True),
+    (2, 20, 512, 512, (8, 8, 2), True, False),
+    (3, 20, 256, 512, (8, 8, 2), False, False),
 ])
 def test_conv3x3_s1(n, hw, cin, cout, tile, residual, post, cluster, block_n):
     _bn_ok(block_n, cout)
@@ -106,7 +110,8 @@ def test_conv3x3_s1(n, hw, cin, cout, tile, residual, post, cluster, block_n):
     _check(out, ref, f"conv3x3 s1 {hw}x{hw} {cin}->{cout} bn{block_n} cl{cluster}")
 
 
-@pytest.mark.parametrize("n,hw,cin,cout,tile", [(3, 80, 64, 128, (8, 8, 2)), (5, 40, 256, 512, (4, 4, 8))])
+@pytest.mark.parametrize("n,hw,cin,cout,tile", [(3, 80, 64, 128, (8, 8, 2)), (5, 40, 256, 512, (4, 4, 8)),
+                                                (1, 40, 256, 512, (16, 8, 1)), (2, 40, 256, 512, (8, 8, 2))])
 def test_conv3x3_s2_phase_in(n, hw, cin, cout, tile, cluster, block_n):
     _bn_ok(block_n, cout)
     torch.manual_seed(2)
