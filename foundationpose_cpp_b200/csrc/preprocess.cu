@@ -367,9 +367,16 @@ constexpr unsigned kDepthMax = 0xFFFFFFFFu - (2200u << 3);
 // The reference keeps these as three [N,V,*] fp32 tensors too (pose_clip, pts_cam, diffuse).
 // Output: one 32-byte record per (hypothesis, vertex): {clip position, (camera-space position, diffuse)} - the
 // rasteriser reads the first half, a shaded pixel both halves of its three vertices as three 32-byte sectors.
-__global__ void vertex_stage_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, float4* __restrict__ vrec) {
+// zfill (may be null): the hypothesis's whole-crop z-buffer of the few-hypotheses path, reset here to "empty" (all ones)
+// by the same CTAs instead of by a launch of its own.
+__global__ void vertex_stage_kernel(DeviceMesh mesh, const PoseAux* __restrict__ aux_all, float4* __restrict__ vrec,
+                                    unsigned long long* __restrict__ zfill) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   const int pose = blockIdx.y;
+  if (zfill) {
+    unsigned long long* z = zfill + (long long)pose * (kCrop * kCrop);
+    for (int i = v; i < kCrop * kCrop; i += gridDim.x * blockDim.x) z[i] = ~0ull;
+  }
   if (v >= mesh.num_vertices) return;
   const PoseAux& a = aux_all[pose];
   const float x = mesh.vertices[3 * v], y = mesh.vertices[3 * v + 1], z = mesh.vertices[3 * v + 2];
@@ -1041,16 +1048,17 @@ int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vre
                   int32_t* rast_id_debug, int* status, unsigned long long* zbuf_scratch, int zbuf_poses,
                   int num_sms, int split_mode, cudaStream_t s) {
   if (n <= 0) return 0;
-  vertex_stage_kernel<<<dim3((mesh.num_vertices + 255) / 256, n), 256, 0, s>>>(mesh, aux, vrec);
   const int sms = num_sms > 0 ? num_sms : 148;
   // band kernel: 2 CTAs per hypothesis and 2 resident CTAs per SM; below ~2 CTAs per SM it is bound by the
   // latency of one CTA walking every triangle (N = 1 and N = 32 take the same ~105 us)
   bool split = n * 4 <= 2 * sms;
   if (split_mode >= 0) split = split_mode != 0;  // tests run both paths on the same input
-  if (split && zbuf_scratch && n <= zbuf_poses) {
-    // few hypotheses: spread the triangles over the machine (see raster_split_kernel)
-    // (a fill kernel rather than cudaMemsetAsync: see clear_status_kernel in session.cu)
-    fill_u64_kernel<<<4 * sms, 256, 0, s>>>(zbuf_scratch, (long long)n * kCrop * kCrop, ~0ull);
+  const bool use_split = split && zbuf_scratch && n <= zbuf_poses;
+  vertex_stage_kernel<<<dim3((mesh.num_vertices + 255) / 256, n), 256, 0, s>>>(mesh, aux, vrec,
+                                                                               use_split ? zbuf_scratch : nullptr);
+  if (use_split) {
+    // few hypotheses: spread the triangles over the machine (see raster_split_kernel); the z-buffers were reset by
+    // the vertex stage
     // one or two triangles per thread: the kernel is a chain of dependent gathers, so its duration is the number of
     // triangles a thread walks (FPB200_SPLIT_SLICES: measurements only)
     static const int force_slices = getenv("FPB200_SPLIT_SLICES") ? atoi(getenv("FPB200_SPLIT_SLICES")) : 0;
@@ -1060,7 +1068,7 @@ int launch_render(const DeviceMesh& mesh, const PoseAux* aux, int n, float4* vre
     static const int shade_rows = getenv("FPB200_SPLIT_SHADE_ROWS") ? atoi(getenv("FPB200_SPLIT_SHADE_ROWS")) : 2;
     shade_split_kernel<<<dim3(kCrop / shade_rows, n), kRenderThreads, 0, s>>>(mesh, aux, vrec, packed, img0,
                                                                              rast_id_debug, zbuf_scratch, shade_rows);
-    return 3;
+    return 2;
   }
   static const int experiment = getenv("FPB200_RENDER_EXPERIMENT") ? atoi(getenv("FPB200_RENDER_EXPERIMENT")) : 0;
   if (experiment == 3) return 1;
