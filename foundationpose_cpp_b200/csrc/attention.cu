@@ -135,6 +135,9 @@ attention_tc_kernel(const __grid_constant__ Params p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // programmatic dependent launch (plan.pdl): the prologue above may overlap the QKV projection's tail; no-ops otherwise
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     int stage = 0;
@@ -573,9 +576,13 @@ const char* build_attention(const __half* qkv, __half* out, int n_hyp, int qkv_l
   if (const char* e = attention_init()) return e;
   if (const char* e = tc::make_params(qkv, out, n_hyp, qkv_ld, out_ld, plan)) return e;
   if (const char* e = tc2::make_params(qkv, out, n_hyp, qkv_ld, out_ld, plan)) return e;
+  plan->grid_v1 = plan->n_items < tc2::device_sms() ? plan->n_items : tc2::device_sms();  // SM count of THIS device
+  {
+    const char* pdl = getenv("FPB200_PDL");  // see conv_gemm.cu: only launches that leave SMs idle
+    plan->pdl = pdl ? pdl[0] == '1' : plan->n_items < tc2::device_sms();
+  }
   // FPB200_ATTN_V2=1 selects the second design (attention2.cu: measured slower so far, kept with its tests - see
   // DESIGN.md section 8); read per plan, never per launch
-  plan->grid_v1 = plan->n_items < tc2::device_sms() ? plan->n_items : tc2::device_sms();  // SM count of THIS device
   const char* v2 = getenv("FPB200_ATTN_V2");
   plan->version = v2 && v2[0] == '1' ? 2 : 1;
   return nullptr;
@@ -595,6 +602,20 @@ void launch_attention(const AttentionPlan& plan, cudaStream_t s) {
   }
   if (plan.version == 2) {
     tc2::launch(prm, s);
+    return;
+  }
+  if (prm.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(prm.grid_v1);
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = tc::kSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, tc::attention_tc_kernel, prm);
     return;
   }
   tc::attention_tc_kernel<<<prm.grid_v1, tc::kThreads, tc::kSmem, s>>>(prm);

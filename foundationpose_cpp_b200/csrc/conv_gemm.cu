@@ -105,6 +105,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (CS > 1) ptx::cluster_sync();  // the peer's barriers are initialised before anything lands on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch (plan.pdl): everything above (barriers, tensor-memory allocation, descriptor prefetch)
+  // touched only this CTA's own state and may run while the producer of this layer's input is still finishing on other
+  // SMs; from here on its output is read.  Both instructions are no-ops in an ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_img;
   const int m_groups = (m_tiles + CS - 1) / CS;
@@ -782,6 +787,13 @@ const char* build_conv_gemm(const ConvGemmDesc& d, ConvGemmPlan* plan) {
   plan->grid = (int)(work < cap ? work : cap) * cluster;
   plan->smem = 1024 + (size_t)p.na * p.a_bytes + (size_t)p.nb * p.b_stage_bytes + kEpiWarps * kStageBytesPerWarp + kBarrierBytes;
   plan->flops = 2.0 * d.n_img * d.out_h * d.out_w * (double)d.cout * d.num_taps * d.cin;
+  {
+    // Programmatic dependent launch where the launch leaves SMs idle (Track, a few hypotheses): the next kernel's CTAs
+    // start there early and hide their launch latency and prologue (Track: +4 %).  Full-size launches gain nothing
+    // (measured at N = 252) and stay ordinary.  FPB200_PDL=0 / 1: never / always (measurements).
+    const char* env = getenv("FPB200_PDL");
+    plan->pdl = env ? env[0] == '1' : plan->grid < g_num_sms;
+  }
   return nullptr;
 }
 
@@ -793,13 +805,15 @@ cudaError_t launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = Cfg<BN, PAIR>::kCS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = plan.pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, PAIR, PER_TAP>, plan.p);
 }
 template <int BN>

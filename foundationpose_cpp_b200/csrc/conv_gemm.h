@@ -103,6 +103,7 @@ struct ConvGemmPlan {
   int mode = 0;     // 0 single CTAs, 2 CTA pairs + cta_group::2
   int grid = 0;
   size_t smem = 0;
+  bool pdl = false;  // launch with programmatic stream serialisation (the kernel waits itself before reading its input)
   double flops = 0;  // 2*M*N*K over valid rows
 };
 

@@ -179,6 +179,9 @@ encoder_block_kernel(const __grid_constant__ EncoderBlockParams p) {
   if (CS > 1) ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // programmatic dependent launch (plan.pdl): the prologue above may overlap the attention kernel's tail
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int n_blocks = (p.rows + kBM - 1) / kBM;
   const int n_items = (n_blocks + CS - 1) / CS;  // work items of a cluster
@@ -691,6 +694,10 @@ const char* build_encoder_block(const EncoderBlockDesc& d, EncoderBlockPlan* pla
   p.dbg_x1 = d.dbg_x1; p.dbg_h = d.dbg_h; p.dbg_y = d.dbg_y;
   p.dbg_clocks = d.dbg_clocks;
   plan->pair = pair;
+  {
+    const char* pdl = getenv("FPB200_PDL");  // see conv_gemm.cu: only launches that leave SMs idle
+    plan->pdl = pdl ? pdl[0] == '1' : n_blocks < g_num_sms;
+  }
   const int items = (n_blocks + cs - 1) / cs;
   const int cap = g_num_sms / cs;
   plan->grid = (items < cap ? items : cap) * cs;
@@ -707,13 +714,15 @@ cudaError_t launch_encoder_block(const EncoderBlockPlan& plan, cudaStream_t stre
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = plan.pair ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = plan.pdl ? 2 : 1;
   cudaError_t e;
   if (plan.p.dbg_clocks)
     e = plan.pair ? cudaLaunchKernelEx(&cfg, encoder_block_kernel<true, true>, plan.p)

@@ -45,6 +45,7 @@ struct EncoderBlockDesc {
 struct EncoderBlockPlan {
   EncoderBlockParams p;
   bool pair = false;
+  bool pdl = false;  // programmatic dependent launch (FPB200_PDL=1: measurements)
   int grid = 0;
   size_t smem = 0;
   int n_hyp = 0;

@@ -19,6 +19,7 @@ struct AttentionPlan {
   CUtensorMap tm_out;  // out as (out_ld, 400, n_hyp), box (64, 32, 1): one softmax warp's rows x one dim half
   int n_items = 0;     // n_hyp * heads * query tiles
   int grid_v1 = 0;     // CTAs of the first kernel: min(n_items, SMs of the plan's device)
+  bool pdl = false;    // programmatic dependent launch (FPB200_PDL=1: measurements)
   unsigned long long* phase_clocks = nullptr;  // optional (FPB200_ATTN_PHASES=1): per-phase clock sums of CTA 0
   // second design (attention2.cu: K / V resident in shared memory, Q in tensor memory, S computed twice)
   CUtensorMap tm_kv64;  // qkv, box (64, 64, 1)
